@@ -1,0 +1,278 @@
+// Scattering, Source and Population for sm_100a.
+//
+//   Scattering  phi_out(nm,g,z) (+)= sum_src sum_gp sigs_z(n(nm),g,gp,z) * phi_src(nm,gp,z)
+//               sigs_z = sum_{mix in z} sigs(mat(mix), n, g+glower_dst, gp+glower_src) * fraction(mix)
+//               (src/Kripke/Kernel/Scattering.cpp:73-99)
+//   Source      phi_out(0,g,zone(mix)) += strength*fraction(mix) for material 0 (Kernel/Source.cpp:59-75)
+//   Population  sum (w(d)*psi(d,g,z))*volume(z)   (Kernel/Population.cpp:49-63)
+//
+// Scattering is kept dense over (g,gp) like the reference.  A thread owns one
+// (moment, zone) pair and a register tile of GT destination groups; the per-zone material mix
+// (<= 3 entries) is held in registers so pure zones -- the overwhelming majority -- take one
+// multiply per sigs entry, which makes sigs_z bit-identical to the reference's 0.0 + sigs*1.0.
+#include "kb200_common.cuh"
+#include <stdlib.h>
+#include <vector>
+
+namespace kb200 {
+
+template <bool EXACT>
+__device__ __forceinline__ double mad2(double a, double b, double c) {
+  if (EXACT) return __dadd_rn(__dmul_rn(a, b), c);
+  return fma(a, b, c);
+}
+
+template <int GT, bool EXACT>
+__global__ void __launch_bounds__(128) scattering_kernel(const kb200_scattering_desc *__restrict__ descs) {
+  const kb200_scattering_desc &ds = descs[blockIdx.z];
+  const int M = ds.M, Gs = ds.Gs, Zs = ds.Zs, G = ds.G;
+  const Strides3 ms = strides_dgz(ds.layout, M, Gs, Zs);
+  const Strides4 ss = strides_sigs(ds.layout, ds.L1, G);
+  // flatten (nm, z) with the faster-varying of the two as the fast thread index
+  const long long total = (long long)M * Zs;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int nm, z;
+  if (ms.a < ms.z) { nm = (int)(t % M); z = (int)(t / M); }
+  else { z = (int)(t % Zs); nm = (int)(t / Zs); }
+  const int n = ds.moment_to_legendre[nm];
+  const int m0 = ds.zone_to_mixelem[z];
+  const int nmix = ds.zone_to_num_mixelem[z];
+  int mat[3] = {0, 0, 0};
+  double frac[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (k < nmix) { mat[k] = ds.mixelem_to_material[m0 + k]; frac[k] = ds.mixelem_to_fraction[m0 + k]; }
+
+  const int g0 = blockIdx.y * GT;
+  double acc[GT];
+#pragma unroll
+  for (int i = 0; i < GT; ++i) acc[i] = 0.0;
+  const long long base = (long long)nm * ms.a + (long long)z * ms.z;
+  for (int s = 0; s < ds.nsrc; ++s) {
+    const double *__restrict__ phi = ds.phi_src[s] + base;
+    const int gl_src = ds.glower_src[s];
+    for (int gp = 0; gp < Gs; ++gp) {
+      const double x = __ldg(phi + (long long)gp * ms.g);
+      const double *__restrict__ sp = ds.sigs + (long long)n * ss.n + (long long)(gp + gl_src) * ss.gp +
+                                      (long long)(g0 + ds.glower_dst) * ss.g;
+#pragma unroll
+      for (int i = 0; i < GT; ++i) {
+        if (g0 + i < Gs) {
+          double sigs_z = 0.0;
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (k < nmix) sigs_z = mad2<EXACT>(__ldg(sp + (long long)mat[k] * ss.mat + (long long)i * ss.g), frac[k], sigs_z);
+          acc[i] = mad2<EXACT>(sigs_z, x, acc[i]);
+        }
+      }
+    }
+  }
+  double *__restrict__ out = ds.phi_out + base;
+#pragma unroll
+  for (int i = 0; i < GT; ++i)
+    if (g0 + i < Gs) {
+      double *q = out + (long long)(g0 + i) * ms.g;
+      *q = ds.accumulate ? __dadd_rn(*q, acc[i]) : acc[i];
+    }
+}
+
+__global__ void source_kernel(const kb200_source_desc *__restrict__ descs) {
+  const kb200_source_desc &ds = descs[blockIdx.z];
+  const Strides3 ms = strides_dgz(ds.layout, ds.M, ds.Gs, ds.Zs);
+  const long long total = (long long)ds.num_mixelem * ds.Gs;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    int mix, g;
+    if (ms.g == 1) { g = (int)(t % ds.Gs); mix = (int)(t / ds.Gs); }
+    else { mix = (int)(t % ds.num_mixelem); g = (int)(t / ds.num_mixelem); }
+    if (ds.mixelem_to_material[mix] == 0) {
+      const int z = ds.mixelem_to_zone[mix];
+      double *q = ds.phi_out + (long long)g * ms.g + (long long)z * ms.z;  // nm = 0
+      *q = __dadd_rn(*q, __dmul_rn(ds.strength, ds.mixelem_to_fraction[mix]));
+    }
+  }
+}
+
+// Population: each block reduces a contiguous segment of one psi chunk; index decode is done on
+// 32-bit segment-relative indices.  Block partials -> d_scratch, then one block sums them in a
+// fixed order (deterministic for a given launch geometry).
+constexpr int kPopThreads = 256;
+constexpr int kPopSeg = 8192;  // elements per block-segment
+constexpr int kPopMaxBlocks = 148 * 16;
+
+__global__ void __launch_bounds__(kPopThreads) population_kernel(const kb200_population_desc *__restrict__ descs, int ndesc,
+                                                                  long long segs_per_desc, double *__restrict__ partials) {
+  __shared__ double red[kPopThreads / 32];
+  double local = 0.0;
+  const long long nseg_total = segs_per_desc * ndesc;
+  for (long long seg = blockIdx.x; seg < nseg_total; seg += gridDim.x) {
+    const int di = (int)(seg / segs_per_desc);
+    const long long sbase = (seg - (long long)di * segs_per_desc) * kPopSeg;
+    const kb200_population_desc &ds = descs[di];
+    const long long total = (long long)ds.Ds * ds.Gs * ds.Zs;
+    const Strides3 fs = strides_dgz(ds.layout, ds.Ds, ds.Gs, ds.Zs);
+    // extents in storage order: n2 fastest
+    long long n1, n2;
+    int role1, role2, role0;  // 0 = direction, 1 = group, 2 = zone
+    {
+      long long st[3] = {fs.a, fs.g, fs.z};
+      long long ex[3] = {ds.Ds, ds.Gs, ds.Zs};
+      int o[3] = {0, 1, 2};
+      for (int a = 0; a < 3; ++a)
+        for (int b = a + 1; b < 3; ++b)
+          if (st[o[b]] > st[o[a]]) { int tmp = o[a]; o[a] = o[b]; o[b] = tmp; }
+      role0 = o[0]; role1 = o[1]; role2 = o[2];
+      n1 = ex[role1]; n2 = ex[role2];
+    }
+    const long long inner = n1 * n2;
+    for (int e = threadIdx.x; e < kPopSeg; e += kPopThreads) {
+      const long long f = sbase + e;
+      if (f >= total) break;
+      const long long i0 = f / inner;
+      const long long rem = f - i0 * inner;
+      const long long i1 = rem / n2, i2 = rem - i1 * n2;
+      long long idx[3];
+      idx[role0] = i0; idx[role1] = i1; idx[role2] = i2;
+      const double v = __ldg(ds.psi + f);
+      local += __dmul_rn(__dmul_rn(__ldg(ds.w + idx[0]), v), __ldg(ds.volume + idx[2]));
+    }
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < kPopThreads / 32) ? red[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) partials[blockIdx.x] = v;
+  }
+}
+
+__global__ void population_final_kernel(const double *__restrict__ partials, int n, double *__restrict__ result, int accumulate) {
+  __shared__ double red[32];
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += partials[i];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double s = (threadIdx.x < (int)(blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) *result = accumulate ? (*result + s) : s;
+  }
+}
+
+__global__ void layout_transform_kernel(int src_layout, int dst_layout, int na, int ng, int nz,
+                                        const double *__restrict__ src, double *__restrict__ dst) {
+  const Strides3 a = strides_dgz(src_layout, na, ng, nz), b = strides_dgz(dst_layout, na, ng, nz);
+  const long long total = (long long)na * ng * nz;
+  // iterate in destination storage order (coalesced writes)
+  long long st[3] = {b.a, b.g, b.z};
+  long long ex[3] = {na, ng, nz};
+  int o[3] = {0, 1, 2};
+  for (int x = 0; x < 3; ++x)
+    for (int y = x + 1; y < 3; ++y)
+      if (st[o[y]] > st[o[x]]) { int tmp = o[x]; o[x] = o[y]; o[y] = tmp; }
+  const long long n2 = ex[o[2]], n1 = ex[o[1]];
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += (long long)gridDim.x * blockDim.x) {
+    long long i0 = f / (n1 * n2), rem = f - i0 * n1 * n2, i1 = rem / n2, i2 = rem - i1 * n2;
+    long long idx[3];
+    idx[o[0]] = i0; idx[o[1]] = i1; idx[o[2]] = i2;
+    dst[f] = src[idx[0] * a.a + idx[1] * a.g + idx[2] * a.z];
+  }
+}
+
+
+}  // namespace kb200
+
+using namespace kb200;
+
+extern "C" {
+
+int kb200_scattering(const kb200_scattering_desc *h, int n, kb200_stream_t stream) {
+  if (n <= 0) return 0;
+  KB_REQUIRE(h, "kb200_scattering: null descriptors");
+  for (int i = 0; i < n; ++i) {
+    KB_REQUIRE(h[i].layout == h[0].layout && h[i].M == h[0].M && h[i].Gs == h[0].Gs && h[i].Zs == h[0].Zs,
+               "kb200_scattering: all descriptors of one call must share their dimensions");
+    KB_REQUIRE(h[i].nsrc >= 1 && h[i].nsrc <= KB200_MAX_DIRSETS, "kb200_scattering: nsrc=%d out of range", h[i].nsrc);
+    KB_REQUIRE(h[i].layout >= 0 && h[i].layout < 6, "kb200_scattering: bad layout %d", h[i].layout);
+    KB_REQUIRE(h[i].phi_out && h[i].sigs && h[i].moment_to_legendre && h[i].zone_to_mixelem && h[i].zone_to_num_mixelem &&
+                   h[i].mixelem_to_material && h[i].mixelem_to_fraction, "kb200_scattering: null pointer in descriptor %d", i);
+  }
+  if (h[0].M <= 0 || h[0].Gs <= 0 || h[0].Zs <= 0) return 0;
+  cudaStream_t st = resolve_stream(stream);
+  const void *d = nullptr;
+  int rc = device_descs(h, sizeof(*h) * n, &d, st);
+  if (rc) return rc;
+  constexpr int GT = 8;
+  long long total = (long long)h[0].M * h[0].Zs;
+  dim3 grid((unsigned)((total + 127) / 128), (h[0].Gs + GT - 1) / GT, n);
+  if (exact_mode()) scattering_kernel<GT, true><<<grid, 128, 0, st>>>((const kb200_scattering_desc *)d);
+  else scattering_kernel<GT, false><<<grid, 128, 0, st>>>((const kb200_scattering_desc *)d);
+  return post_launch("scattering");
+}
+
+int kb200_source(const kb200_source_desc *h, int n, kb200_stream_t stream) {
+  if (n <= 0) return 0;
+  KB_REQUIRE(h, "kb200_source: null descriptors");
+  long long maxwork = 0;
+  for (int i = 0; i < n; ++i) {
+    KB_REQUIRE(h[i].layout >= 0 && h[i].layout < 6, "kb200_source: bad layout %d", h[i].layout);
+    long long w = (long long)h[i].num_mixelem * h[i].Gs;
+    if (w > maxwork) maxwork = w;
+  }
+  if (maxwork == 0) return 0;
+  cudaStream_t st = resolve_stream(stream);
+  const void *d = nullptr;
+  int rc = device_descs(h, sizeof(*h) * n, &d, st);
+  if (rc) return rc;
+  long long blocks = (maxwork + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  dim3 grid((unsigned)blocks, 1, n);
+  source_kernel<<<grid, 256, 0, st>>>((const kb200_source_desc *)d);
+  return post_launch("source");
+}
+
+size_t kb200_population_scratch_doubles(void) { return kPopMaxBlocks; }
+
+int kb200_population(const kb200_population_desc *h, int n, double *d_scratch, double *d_result, kb200_stream_t stream) {
+  KB_REQUIRE(d_result && d_scratch, "kb200_population: null result/scratch");
+  cudaStream_t st = resolve_stream(stream);
+  if (n <= 0) {
+    KB_CUDA(cudaMemsetAsync(d_result, 0, sizeof(double), st));
+    return 0;
+  }
+  KB_REQUIRE(h, "kb200_population: null descriptors");
+  long long maxtotal = 0;
+  for (int i = 0; i < n; ++i) {
+    KB_REQUIRE(h[i].layout >= 0 && h[i].layout < 6, "kb200_population: bad layout %d", h[i].layout);
+    long long t = (long long)h[i].Ds * h[i].Gs * h[i].Zs;
+    if (t > maxtotal) maxtotal = t;
+  }
+  const void *d = nullptr;
+  int rc = device_descs(h, sizeof(*h) * n, &d, st);
+  if (rc) return rc;
+  long long segs_per_desc = (maxtotal + kPopSeg - 1) / kPopSeg;
+  if (segs_per_desc == 0) segs_per_desc = 1;
+  long long nseg = segs_per_desc * n;
+  int blocks = (int)(nseg < kPopMaxBlocks ? nseg : kPopMaxBlocks);
+  population_kernel<<<blocks, kPopThreads, 0, st>>>((const kb200_population_desc *)d, n, segs_per_desc, d_scratch);
+  rc = post_launch("population");
+  if (rc) return rc;
+  population_final_kernel<<<1, 256, 0, st>>>(d_scratch, blocks, d_result, 0);
+  return post_launch("population_final");
+}
+
+int kb200_layout_transform(int src_layout, int dst_layout, int na, int ng, int nz, const double *src, double *dst,
+                           kb200_stream_t stream) {
+  KB_REQUIRE(src_layout >= 0 && src_layout < 6 && dst_layout >= 0 && dst_layout < 6, "kb200_layout_transform: bad layout");
+  KB_REQUIRE(src && dst && src != dst, "kb200_layout_transform: bad pointers (out-of-place only)");
+  long long total = (long long)na * ng * nz;
+  if (total <= 0) return 0;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  layout_transform_kernel<<<(unsigned)blocks, 256, 0, resolve_stream(stream)>>>(src_layout, dst_layout, na, ng, nz, src, dst);
+  return post_launch("layout_transform");
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C++ host layer and the C ABI, against
+the CPU oracle on identical seeded inputs and against the reference's golden vectors.
+
+Tolerances (BASELINE.json north_star): per-iteration particle count and ||phi||_2 within 1e-12
+relative (fp64 re-ordering / FMA contraction only).  With kb200_set_exact(1) the kernels keep the
+reference's multiply-then-add arithmetic and summation order, and every field must then be
+BIT-identical to the oracle (which is bit-identical to the reference's Sequential path)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from conftest import oracle_problem
+
+pytestmark = pytest.mark.gpu
+LAYOUTS = ["DGZ", "DZG", "GDZ", "GZD", "ZDG", "ZGD"]
+RTOL = 1e-12
+
+
+def seeded(n, seed, lo=0.0, hi=1.0):
+    return np.random.default_rng(seed).uniform(lo, hi, n)
+
+
+def fill_both(p, o, field, seed, lo=0.0, hi=1.0):
+    for c in range(o.num_chunks(field)):
+        v = seeded(len(o.chunk(field, c)), seed + c, lo, hi)
+        o.chunk(field, c)[:] = v
+        p.set_chunk(field, c, v)
+
+
+def assert_close(got, ref, what, exact):
+    assert got.shape == ref.shape, what
+    if exact:
+        assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), f"{what}: not bit-identical"
+    else:
+        scale = max(float(np.max(np.abs(ref))), 1e-300)
+        err = float(np.max(np.abs(got - ref))) / scale
+        assert err <= RTOL, f"{what}: max rel err {err:.3e}"
+
+
+def pair(gpu, args):
+    p = gpu.Problem(args)
+    o, niter, bj = oracle_problem(args)
+    return p, o, niter, bj
+
+
+SMALL = "--zones 12,8,10 --groups 8 --quad 32 --legendre 3 --gset 2 --dset 8 --zset 2,1,2"
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_ltimes(gpu, layout, exact):
+    gpu.abi().kb200_set_exact(int(exact))
+    p, o, _, _ = pair(gpu, f"{SMALL} --layout {layout}")
+    fill_both(p, o, "psi", 100, -1.0, 2.0)
+    o.zero("phi"); o.ltimes()
+    p.call("zero:phi"); p.call("LTimes")
+    assert_close(p.field("phi"), o.field("phi"), f"LTimes {layout}", exact)
+    gpu.abi().kb200_set_exact(0)
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_lplustimes(gpu, layout, exact):
+    gpu.abi().kb200_set_exact(int(exact))
+    p, o, _, _ = pair(gpu, f"{SMALL} --layout {layout}")
+    fill_both(p, o, "phi_out", 200, -1.0, 1.0)
+    o.zero("rhs"); o.lplustimes()
+    p.call("zero:rhs"); p.call("LPlusTimes")
+    assert_close(p.field("rhs"), o.field("rhs"), f"LPlusTimes {layout}", exact)
+    gpu.abi().kb200_set_exact(0)
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_scattering_and_source_with_dense_asymmetric_sigs(gpu, layout, exact):
+    """the shipped sigs is diagonal, which would hide a g/gp swap: use a dense random one."""
+    gpu.abi().kb200_set_exact(int(exact))
+    p, o, _, _ = pair(gpu, f"{SMALL} --layout {layout}")
+    fill_both(p, o, "data/sigs", 300, 0.0, 0.1)
+    fill_both(p, o, "phi", 400, -1.0, 1.0)
+    o.zero("phi_out"); o.scattering(); o.source()
+    p.call("zero:phi_out"); p.call("scattering"); p.call("source")
+    assert_close(p.field("phi_out"), o.field("phi_out"), f"scattering+source {layout}", exact)
+    gpu.abi().kb200_set_exact(0)
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_sweep_subdomain_with_incoming_faces(gpu, layout, exact):
+    """single-subdomain entry point with non-zero incoming face fluxes on all three planes."""
+    gpu.abi().kb200_set_exact(int(exact))
+    p, o, _, _ = pair(gpu, f"{SMALL} --layout {layout}")
+    fill_both(p, o, "rhs", 500, 0.0, 1.0)
+    for f, s in (("i_plane", 600), ("j_plane", 700), ("k_plane", 800)):
+        fill_both(p, o, f, s, 0.0, 0.5)
+    for sdom in (0, 5, o.num_subdomains() - 1):
+        o.sweep_subdomain(sdom)
+        p.call(f"sweepSubdomain:{sdom}")
+    for f in ("psi", "i_plane", "j_plane", "k_plane"):
+        got, ref = p.field(f), o.field(f)
+        if f == "psi":  # only the swept subdomains are defined
+            n = len(o.chunk("psi", 0))
+            for sdom in (0, 5, o.num_subdomains() - 1):
+                assert_close(got[sdom * n:(sdom + 1) * n], ref[sdom * n:(sdom + 1) * n], f"sweep psi {layout}", exact)
+        else:
+            assert_close(got, ref, f"sweep {f} {layout}", exact)
+    gpu.abi().kb200_set_exact(0)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_sweep_solver_and_population(gpu, layout):
+    p, o, _, _ = pair(gpu, f"{SMALL} --layout {layout}")
+    fill_both(p, o, "rhs", 900, 0.0, 1.0)
+    o.sweep_solver(False)
+    p.call("SweepSolver")
+    for f in ("psi", "i_plane", "j_plane", "k_plane"):
+        assert_close(p.field(f), o.field(f), f"SweepSolver {f} {layout}", False)
+    ref = o.population()
+    got = p.call("population")
+    assert abs(got - ref) <= RTOL * abs(ref)
+
+
+@pytest.mark.parametrize("name", ["G1_default", "G1z_zset222", "G3_legendre9", "G4_kba_proxy", "G4b_undecomposed",
+                                  "G5_block_jacobi", "G6_gauss_legendre_4x4", "G6b_gauss_legendre_8x8", "R1_ragged",
+                                  "R2_legendre0", "R3_custom_xs", "L_DGZ", "L_DZG", "L_GDZ", "L_GZD", "L_ZDG", "L_ZGD"])
+def test_full_solve_matches_reference_goldens(gpu, goldens, name):
+    """Kripke::SteadyStateSolver on the GPU vs numbers the unmodified reference produced."""
+    g = goldens[name]
+    p = gpu.Problem(g["args"])
+    parts = p.solve()
+    assert len(parts) == len(g["particles"])
+    for it, (a, b) in enumerate(zip(parts, g["particles"])):
+        assert abs(a - b) <= RTOL * abs(b), f"{name} iter {it}: {a!r} vs {b!r}"
+    for f in ("phi", "psi", "rhs", "phi_out"):
+        v = p.field(f).astype(np.longdouble)
+        l2 = float(np.sqrt(np.sum(v * v)))
+        ref = g["norms"][f]
+        assert len(v) == ref["n"]
+        assert abs(l2 - ref["l2"]) <= RTOL * ref["l2"], f"{name} ||{f}||"
+
+
+@pytest.mark.parametrize("layout", ["DGZ", "GZD", "ZGD"])
+def test_full_solve_bit_exact_mode(gpu, layout):
+    """exact mode: psi, phi, rhs, phi_out after 3 iterations are bit-identical to the oracle."""
+    gpu.abi().kb200_set_exact(1)
+    try:
+        args = f"--zones 8,8,8 --groups 8 --quad 16 --legendre 2 --gset 2 --zset 2,2,1 --niter 3 --layout {layout}"
+        p, o, niter, bj = pair(gpu, args)
+        got = p.solve()
+        ref = o.solve(niter, bj)
+        for a, b in zip(got, ref):
+            assert abs(a - b) <= 1e-13 * abs(b)
+        for f in ("psi", "phi", "rhs", "phi_out", "i_plane", "j_plane", "k_plane"):
+            assert_close(p.field(f), o.field(f), f"{f} {layout}", True)
+    finally:
+        gpu.abi().kb200_set_exact(0)
+
+
+def test_reference_visit_order_mode(gpu, monkeypatch):
+    """KB200_SWEEP_ORDER=reference: one subdomain at a time in the reference's queue order gives the same psi."""
+    args = "--zones 8,8,8 --groups 4 --quad 16 --legendre 1 --gset 1 --dset 8 --zset 2,2,1 --niter 2"
+    p1 = gpu.Problem(args)
+    a = p1.solve()
+    monkeypatch.setenv("KB200_SWEEP_ORDER", "reference")
+    p2 = gpu.Problem(args)
+    b = p2.solve()
+    assert a == b
+    assert np.array_equal(p1.field("psi"), p2.field("psi"))
+
+
+def test_decomposition_invariance_at_scale(gpu):
+    """size-independent property on a problem too big for the scalar oracle
+    in test time: 32^3 x 32 groups x 96 directions, zset 1,1,1 vs 4,2,2 / gset 1 vs 4."""
+    base = "--zones 32,32,32 --groups 32 --quad 96 --legendre 4 --niter 3 --layout ZGD"
+    a = gpu.Problem(base + " --zset 1,1,1 --gset 1").solve()
+    b = gpu.Problem(base + " --zset 4,2,2 --gset 4").solve()
+    for x, y in zip(a, b):
+        assert abs(x - y) <= RTOL * abs(y)
+
+
+def test_layout_transform_round_trip(gpu):
+    A = gpu.abi()
+    na, ng, nz = 6, 5, 77
+    n = na * ng * nz
+    src = seeded(n, 42)
+    bufs = [C.c_void_p() for _ in range(3)]
+    for b in bufs:
+        assert A.kb200_alloc(n * 8, C.byref(b)) == 0
+    A.kb200_upload(bufs[0], src.ctypes.data_as(C.c_void_p), n * 8, None)
+    for dst in range(6):
+        assert A.kb200_layout_transform(0, dst, na, ng, nz, bufs[0], bufs[1], None) == 0
+        assert A.kb200_layout_transform(dst, 0, na, ng, nz, bufs[1], bufs[2], None) == 0
+        out = np.empty(n)
+        A.kb200_download(out.ctypes.data_as(C.c_void_p), bufs[2], n * 8, None)
+        A.kb200_stream_sync(None)
+        assert np.array_equal(out, src)
+        mid = np.empty(n)
+        A.kb200_download(mid.ctypes.data_as(C.c_void_p), bufs[1], n * 8, None)
+        A.kb200_stream_sync(None)
+        cube = src.reshape(na, ng, nz)
+        perm = {0: (0, 1, 2), 1: (0, 2, 1), 2: (1, 0, 2), 3: (1, 2, 0), 4: (2, 0, 1), 5: (2, 1, 0)}[dst]
+        assert np.array_equal(mid, np.ascontiguousarray(cube.transpose(perm)).ravel())
+    for b in bufs:
+        A.kb200_free(b)
