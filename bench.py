@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- Kripke source-iteration hot path on B200: grind time per unknown per iteration.
+
+  python bench.py --gpus 1 --steps K --warmup W              our arm (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...     the unmodified reference on the host CPUs
+  torchrun --nproc-per-node N ... bench.py --gpus N ...       one rank per GPU (NCCL over NVLink)
+
+A "step" is one source iteration (LTimes, Scattering, Source, LPlusTimes, SweepSolver, Population)
+of BASELINE.json configs[1] per GPU: 64^3 zones x 64 groups x 192 directions, Legendre order 4,
+pmethod sweep (3.22e9 unknowns, 59.5 GB of fields: far larger than the 126 MB L2, so no flush is
+needed between iterations).  For N>1 the same per-GPU block is tiled with --procs (weak scaling,
+KBA sweep with face exchange over NCCL).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PROCS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+WORKLOADS = {
+    # name: (zones per GPU, groups, directions, legendre, extra flags)
+    "config2": ((64, 64, 64), 64, 192, 4, ""),                 # BASELINE configs[1] (headline)
+    "config1": ((16, 16, 16), 32, 96, 4, ""),                  # configs[0], the reference's default
+    "config3": ((32, 32, 32), 128, 128, 9, ""),                # configs[2], high scattering order
+    "config5": ((64, 64, 64), 32, 96, 4, "--pmethod bj"),      # configs[4], block Jacobi weak scaling
+    "small": ((32, 32, 32), 32, 96, 4, ""),
+}
+
+
+def kripke_args(workload, n_gpus, layout, niter, zones_override=None):
+    zones, groups, dirs, leg, extra = WORKLOADS[workload]
+    if zones_override:
+        zones = zones_override
+    px, py, pz = PROCS[n_gpus]
+    gz = (zones[0] * px, zones[1] * py, zones[2] * pz)
+    a = f"--zones {gz[0]},{gz[1]},{gz[2]} --groups {groups} --quad {dirs} --legendre {leg} --layout {layout} " \
+        f"--procs {px},{py},{pz} --niter {niter} {extra}"
+    return a.split(), groups * dirs * gz[0] * gz[1] * gz[2]
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.max_mhz, self.reasons = [], None, set()
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                               "-i", str(self.index)], text=True, timeout=5).strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=3)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_reference_cpu(workload, layout, steps, warmup, zones):
+    """times the unmodified reference (oracle/_ref/kripke_ref, OpenMP, all host threads) on a bounded
+    sample of the workload: same groups/directions/legendre/layout, fewer zones."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "kripke_ref")
+    cores = os.cpu_count() or 1
+    groups, dirs, leg, extra = WORKLOADS[workload][1:]
+    if not os.path.exists(ref):
+        return None
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="spread", OMP_PLACES="cores")
+    cmd = [ref, "--arch", "OpenMP", "--layout", layout, "--zones", "%d,%d,%d" % zones, "--groups", str(groups),
+           "--quad", str(dirs), "--legendre", str(leg), "--niter", str(steps + warmup), "--time"] + extra.split()
+    out = subprocess.check_output(cmd, text=True, env=env)
+    times = [float(l.split()[2]) for l in out.splitlines() if l.startswith("ITER_TIME")]
+    timers = {l.split()[1]: float(l.split()[2]) for l in out.splitlines() if l.startswith("TIMER ")}
+    unknowns = groups * dirs * zones[0] * zones[1] * zones[2]
+    t = sum(times[warmup:]) / max(1, len(times[warmup:]))
+    return {"value": 1e9 * t / unknowns, "unit": "ns/(unknown*iter)", "cores": cores, "kind": "reference",
+            "sample": f"unmodified reference (OpenMP, {cores} threads), zones {zones[0]}x{zones[1]}x{zones[2]} of the "
+                      f"workload's {groups} groups x {dirs} directions, {len(times[warmup:])} timed iterations after {warmup} warm-up",
+            "s_per_iter": t, "unknowns": unknowns, "kernel_seconds_total": timers}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--layout", default=os.environ.get("KB200_BENCH_LAYOUT", "DGZ"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-zones", default="32,32,32", help="zones of the CPU sample for --impl reference")
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = args.gpus
+    if world > 1 and world != n_gpus:
+        sys.exit(f"--gpus {n_gpus} but WORLD_SIZE={world}")
+
+    kargs, unknowns = kripke_args(args.workload, n_gpus, args.layout, args.steps + warmup)
+    config = {"workload": f"Kobayashi-3i synthetic, BASELINE {args.workload}: {' '.join(kargs)} "
+                          f"({WORKLOADS[args.workload][0][0]}^3 zones per GPU)",
+              "layout": args.layout, "unknowns": unknowns, "l2_policy": "inputs larger than L2 (59.5 GB of fields per GPU)",
+              "parallelism": f"kba{n_gpus}" if n_gpus > 1 else "single"}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        zones = tuple(int(x) for x in args.ref_zones.split(","))
+        r = run_reference_cpu(args.workload, args.layout, args.steps, warmup, zones)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/kripke_ref was not built"}))
+            return
+        line = {"impl": "reference", "metric": "grind_time", "value": r["value"], "unit": r["unit"], "n_gpus": n_gpus,
+                "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * r["s_per_iter"], "higher_is_better": False,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "throughput_unknowns_per_s": 1e9 / r["value"],
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "kernel_seconds_total": r["kernel_seconds_total"]}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import numpy as np
+    import kripke_b200 as kb
+    A, H = kb.abi(), kb.host()
+    kb.init_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            kb.api.check(A.kb200_comm_unique_id(buf), "kb200_comm_unique_id")
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        raw = bytes(uid.cpu().tolist())
+        kb.api.check(A.kb200_comm_init(rank, world, raw), "kb200_comm_init")
+        H.kripke_b200_set_world(rank, world)
+
+    def barrier():
+        A.kb200_device_sync()
+        if dist is not None:
+            dist.barrier()
+
+    H.kripke_b200_timer_sync(0)
+    p = kb.Problem(kargs)
+
+    # e2e staging: every generated input table of the step lives in pinned host memory and is
+    # re-uploaded inside the timed region (cross sections, material mix, quadrature, L/L+)
+    step_inputs = ["sigt_zonal", "data/sigs", "ell", "ell_plus", "quadrature/xcos", "quadrature/ycos", "quadrature/zcos",
+                   "quadrature/w", "volume", "dx", "dy", "dz", "zone_to_mixelem", "zone_to_num_mixelem",
+                   "mixelem_to_zone", "mixelem_to_material", "mixelem_to_fraction", "moment_to_legendre"]
+    staged, h2d_bytes = [], 0
+    for name in step_inputs:
+        for c in range(p.num_chunks(name)):
+            arr = p.chunk(name, c)
+            nbytes = arr.nbytes
+            if nbytes == 0:
+                continue
+            hp = C.c_void_p()
+            kb.api.check(A.kb200_alloc_host(nbytes, C.byref(hp)))
+            C.memmove(hp, arr.ctypes.data, nbytes)
+            staged.append((name, c, hp, nbytes))
+            h2d_bytes += nbytes
+
+    def upload_inputs():
+        for name, c, hp, nbytes in staged:
+            A.kb200_upload(p.device_ptr(name, c, True), hp, nbytes, None)
+
+    kernels = ["LTimes", "scattering", "source", "LPlusTimes", "SweepSolver", "population"]
+    ev = {}
+    for k in kernels:
+        a, b = C.c_void_p(), C.c_void_p()
+        A.kb200_event_create(C.byref(a)); A.kb200_event_create(C.byref(b))
+        ev[k] = (a, b)
+    ev_step = (C.c_void_p(), C.c_void_p())
+    A.kb200_event_create(C.byref(ev_step[0])); A.kb200_event_create(C.byref(ev_step[1]))
+    ktime = {k: [] for k in kernels}
+    particles = []
+
+    def step(timed, with_h2d):
+        if with_h2d:
+            upload_inputs()
+        for z, k in (("phi", "LTimes"), ("phi_out", "scattering"), (None, "source"), ("rhs", "LPlusTimes"),
+                     (None, "SweepSolver"), (None, "population")):
+            if z:
+                p.call("zero:" + z)
+            if timed:
+                A.kb200_event_record(ev[k][0], None)
+            r = p.call(k)
+            if timed:
+                A.kb200_event_record(ev[k][1], None)
+            if k == "population":
+                particles.append(r)  # 8-byte device->host read of the step's result
+        if timed:
+            A.kb200_device_sync()
+            for k in kernels:
+                ms = C.c_float()
+                A.kb200_event_elapsed_ms(ev[k][0], ev[k][1], C.byref(ms))
+                ktime[k].append(ms.value)
+
+    p.call("zero:psi")
+    for _ in range(warmup):
+        step(False, True)
+
+    # ---- timed region A: device-resident ("value") ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    cnt0 = C.c_uint64()
+    A.kb200_launch_count(C.byref(cnt0), 1)
+    barrier()
+    A.kb200_event_record(ev_step[0], None)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(True, False)
+    A.kb200_event_record(ev_step[1], None)
+    barrier()
+    wall_dev = time.perf_counter() - t0
+    ms = C.c_float()
+    A.kb200_event_elapsed_ms(ev_step[0], ev_step[1], C.byref(ms))
+    launches = C.c_uint64()
+    A.kb200_launch_count(C.byref(launches), 0)
+    dev_s = ms.value * 1e-3
+
+    # ---- timed region B: end to end through the host API with host buffers ("e2e") ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(False, True)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.result()
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_s, e2e_s, wall_dev], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s, wall_dev = t.tolist()
+
+    if rank == 0:
+        Z = unknowns // (WORKLOADS[args.workload][1] * WORKLOADS[args.workload][2])
+        G, D, L = WORKLOADS[args.workload][1], WORKLOADS[args.workload][2], WORKLOADS[args.workload][3]
+        M = (L + 1) ** 2
+        N_u, N_m = float(unknowns), float(M * G * Z)
+        # algorithmic bytes per launch, per GPU (SURVEY 8d3 / DESIGN.md)
+        alg = {"LTimes": 8 * N_u + 8 * N_m, "LPlusTimes": 8 * N_u + 8 * N_m, "scattering": 16 * N_m,
+               "SweepSolver": 16 * N_u, "population": 8 * N_u, "source": 0.0}
+        flops = {"LTimes": 2 * M * N_u, "LPlusTimes": 2 * M * N_u, "scattering": 2 * G * N_m}
+        peak, peak_src = measured_peaks()
+        per_kernel = {}
+        for k in kernels:
+            ms_k = statistics.mean(ktime[k]) if ktime[k] else None
+            per_kernel[k] = {"ms": ms_k, "alg_GBs_per_gpu": (alg[k] / n_gpus / (ms_k * 1e-3) / 1e9) if ms_k else None,
+                             "frac_of_hbm_peak": (alg[k] / n_gpus / (ms_k * 1e-3) / 1e9 / peak) if ms_k else None}
+            if k in flops and ms_k:
+                per_kernel[k]["fp64_TFLOPs_per_gpu"] = flops[k] / n_gpus / (ms_k * 1e-3) / 1e12
+        dom = max(kernels, key=lambda k: per_kernel[k]["ms"] or 0)
+        grind_ns = 1e9 * dev_s / args.steps / unknowns
+        e2e_ns = 1e9 * e2e_s / args.steps / unknowns
+        line = {"metric": "grind_time", "value": grind_ns, "unit": "ns/(unknown*iter)", "n_gpus": n_gpus,
+                "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": False,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "throughput_unknowns_per_s": unknowns / (dev_s / args.steps),
+                "e2e": {"value": e2e_ns, "unit": "ns/(unknown*iter)", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
+                        "ms_per_step": 1e3 * e2e_s / args.steps,
+                        "what": "source iteration through the C++ Kripke:: host layer; all generated input tables "
+                                "re-uploaded from pinned host memory and the particle count read back every step"},
+                "gpu_launches": int(launches.value),
+                "clocks": clocks,
+                "roofline": {"kernel": dom, "bound": "hbm", "achieved": per_kernel[dom]["alg_GBs_per_gpu"], "peak": peak,
+                             "unit": "GB/s", "frac": per_kernel[dom]["frac_of_hbm_peak"], "traffic": None,
+                             "peak_source": peak_src},
+                "per_kernel": per_kernel,
+                "particles_last": particles[-1] if particles else None,
+                "wall_ms_per_step_device_region": 1e3 * wall_dev / args.steps}
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            try:
+                r = run_reference_cpu(args.workload, args.layout, 2, 1, (16, 16, 16))
+                if r:
+                    line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:  # the baseline is reported, never required
+                line["cpu_baseline"] = {"error": str(e)}
+        print(json.dumps(line))
+    p.close()
+    if dist is not None:
+        A.kb200_comm_destroy()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -122,6 +122,7 @@ int main(int argc, char **argv) {
   }
 
   auto t0 = std::chrono::steady_clock::now();
+  auto t_prev = t0;
   Kernel::kConst(ds.getVariable<Field_Flux>("psi"), 0.0);
   for (int it = 0; it < v.niter; ++it) {
     Kernel::kConst(ds.getVariable<Field_Moments>("phi"), 0.0);
@@ -134,7 +135,13 @@ int main(int argc, char **argv) {
     std::vector<SdomId> l(ns);
     for (SdomId i{0}; i < ns; ++i) l[*i] = i;
     SweepSolver(ds, l, bj);
-    printf("ITER %d particles=%.17g\n", it, Kernel::population(ds));
+    double part = Kernel::population(ds);
+    printf("ITER %d particles=%.17g\n", it, part);
+    if (timeit) {
+      auto tn = std::chrono::steady_clock::now();
+      printf("ITER_TIME %d %.6f\n", it, std::chrono::duration<double>(tn - t_prev).count());
+      t_prev = tn;
+    }
   }
   auto t1 = std::chrono::steady_clock::now();
 
