@@ -109,6 +109,45 @@ def test_sweep_subdomain_with_incoming_faces(gpu, layout, exact):
     gpu.abi().kb200_set_exact(0)
 
 
+ZLINE_CASES = [
+    # zone-fastest layouts with ni % 4 == 0 take the line-streaming kernel (kb200_sweep_zline.cu)
+    "--zones 16,40,20 --groups 4 --quad 16 --legendre 1 --gset 1 --dset 8 --zset 1,1,1",   # 2x2 column tiles, ragged
+    "--zones 8,8,4 --groups 6 --quad 24 --legendre 1 --gset 1 --dset 8 --zset 1,1,1",      # packed sub-streams
+    "--zones 32,16,48 --groups 4 --quad 16 --legendre 1 --gset 2 --dset 8 --zset 2,1,3",   # decomposed, 16^3 subdomains
+    "--zones 4,33,17 --groups 3 --quad 8 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",     # one-lane / one-warp tiles
+]
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("layout", ["DGZ", "GDZ"])
+@pytest.mark.parametrize("case", range(len(ZLINE_CASES)))
+def test_sweep_zone_fastest_line_kernel(gpu, case, layout, exact):
+    gpu.abi().kb200_set_exact(int(exact))
+    try:
+        p, o, _, _ = pair(gpu, f"{ZLINE_CASES[case]} --layout {layout}")
+        fill_both(p, o, "rhs", 1500 + case, 0.0, 1.0)
+        for f, s in (("i_plane", 1600), ("j_plane", 1700), ("k_plane", 1800)):
+            fill_both(p, o, f, s, 0.0, 0.5)
+        n = len(o.chunk("psi", 0))
+        sdoms = sorted(set([0, 3, o.num_subdomains() // 2, o.num_subdomains() - 1]))
+        for sdom in sdoms:  # every entry point call sees non-zero inflow on all three faces
+            o.sweep_subdomain(sdom)
+            p.call(f"sweepSubdomain:{sdom}")
+        got = p.field("psi"); ref = o.field("psi")
+        for sdom in sdoms:
+            assert_close(got[sdom * n:(sdom + 1) * n], ref[sdom * n:(sdom + 1) * n], f"zline psi {layout} sdom {sdom}", exact)
+        for f in ("i_plane", "j_plane", "k_plane"):
+            assert_close(p.field(f), o.field(f), f"zline {f} {layout}", exact)
+        # the batched solver (all octants, on-rank face delivery) on top of a fresh rhs
+        fill_both(p, o, "rhs", 1900 + case, 0.0, 1.0)
+        o.sweep_solver(False)
+        p.call("SweepSolver")
+        for f in ("psi", "i_plane", "j_plane", "k_plane"):
+            assert_close(p.field(f), o.field(f), f"zline SweepSolver {f} {layout}", exact)
+    finally:
+        gpu.abi().kb200_set_exact(0)
+
+
 @pytest.mark.parametrize("layout", LAYOUTS)
 def test_sweep_solver_and_population(gpu, layout):
     p, o, _, _ = pair(gpu, f"{SMALL} --layout {layout}")
