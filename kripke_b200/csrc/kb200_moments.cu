@@ -283,6 +283,9 @@ struct MomentsDescK {
 
 using namespace kb200;
 
+int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, int nsets, int accumulate, const void *d_views,
+                          int n, const void *const *h_ptrs, int n_ptrs, cudaStream_t st);  // kb200_moments_mma.cu
+
 namespace {
 
 struct TileChoice { int OT, OTP, ntiles; };
@@ -359,6 +362,18 @@ static int run_moments(int mode, int layout, int M, int Ds, int Gs, int Zs, int 
   const void *d_views = nullptr;
   rc = device_descs(views.data(), sizeof(MomentsDescK) * n, &d_views, st);
   if (rc) return rc;
+
+  if (!exact_mode()) {  // default arithmetic: fp64 tensor-core path for the (group,zone)-contiguous layouts
+    std::vector<const void *> ptrs;
+    for (int i = 0; i < n; ++i) {
+      const char *hb = (const char *)h_descs + desc_stride * i;
+      const void *const *tin = (const void *const *)(hb + off_in), *const *tout = (const void *const *)(hb + off_out);
+      for (int s = 0; s < (mode == 0 ? nsets : 1); ++s) ptrs.push_back(tin[s]);
+      for (int s = 0; s < (mode == 0 ? 1 : nsets); ++s) ptrs.push_back(tout[s]);
+    }
+    rc = kb200_moments_mma_try(mode, layout, M, Ds, Gs, Zs, nsets, accumulate, d_views, n, ptrs.data(), (int)ptrs.size(), st);
+    if (rc >= 0) return rc;
+  }
 
   MomentsGeom gm;
   memset(&gm, 0, sizeof(gm));

@@ -1,0 +1,247 @@
+// LTimes / LPlusTimes on the fp64 tensor-core pipe (mma.sync m8n8k4 f64) for the storage orders whose
+// long (group, zone) run is contiguous: DGZ, DZG, GDZ.
+//
+//   out[o][n] (+)= sum_k W[o][k] * in[k][n]        n = contiguous run of N elements, per batch b
+//   LTimes      o = moment,              k = (direction set, direction)     (Kernel/LTimes.cpp:54-65)
+//   LPlusTimes  o = (direction set, dir), k = moment                        (Kernel/LPlusTimes.cpp:49-60)
+//
+// Why tensor cores: at BASELINE config 2 both kernels sit on the HBM/fp64 ridge (5.5 flop/B with a
+// measured 36.9 TFLOP/s DFMA peak and 6.5 TB/s HBM), so the contraction has to run near the fp64
+// peak to stay bandwidth-bound.  A DFMA formulation needs one shared-memory weight operand per
+// four DFMAs and saturates the LSU/issue ports first; DMMA issues 1/8 of the instructions and takes
+// one 8-byte fragment load per 8x8x4 tile (ncu evidence in profiles/).
+//
+// Structure: persistent CTAs of 8 warps walk n-tiles of 64*NB columns.  The streamed operand is
+// brought in by a 3-stage cp.async pipeline as [KC rows][tile] slabs (rows padded so that the
+// 4x8 B-fragment read is bank-conflict free); the weights are converted once per CTA into
+// fragment-major shared memory (one coalesced 8-byte read per A fragment).  Each warp owns 8*NB
+// columns and keeps QP o-tiles of accumulators in registers.  Two regimes:
+//   * K streamed, all outputs resident in registers   (LTimes: O = M small, K = D large)
+//   * K resident (one slab per tile), outputs in passes of QP o-tiles over the same slab
+//                                                      (LPlusTimes: K = M small, O = D large)
+// Rows/columns beyond O, K are zero padded.  This path is not bit-ordered like the reference (the
+// tensor core sums four products per step); EXACT mode uses the DFMA kernels in kb200_moments.cu.
+#include "kb200_common.cuh"
+
+namespace kb200 {
+
+struct MomentsDescK {  // same as in kb200_moments.cu: pointer tables inside the device copy of the ABI descriptor
+  const double *const *w;
+  const double *const *in;
+  double *const *out;
+};
+
+struct MmaGeom {
+  int mode;  // 0 = LTimes, 1 = LPlusTimes
+  int M, Ds, nsets;
+  int O, K, q, nkc4;  // outputs, reduction length, o-tiles (8), k-chunks (4)
+  int KC;             // rows per stage slab (multiple of 4)
+  int nst;            // slabs per tile
+  int npass;          // output passes per tile (npass > 1 only if nst == 1)
+  int accumulate;
+  long long B, N;     // batches, contiguous run
+  long long in_b, in_r, out_b, out_r;  // batch / row strides of the streamed and the produced field
+  long long ntn;      // tiles along n
+};
+
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int MMA_STAGES = 3;
+
+template <int QP, int NB>
+__global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(const MomentsDescK *__restrict__ descs, MmaGeom gm) {
+  extern __shared__ __align__(16) double msm[];
+  constexpr int NT = 64 * NB, NTP = NT + 4;  // row stride = 4 (mod 16) doubles: conflict-free B fragments
+  constexpr int PPR = NT / 2;                // 16-byte pieces per slab row
+  constexpr int RPP = 256 / PPR;             // slab rows filled per pass of the CTA
+  double *Ws = msm;                                         // [nkc4][q][32] fragment-major weights
+  double *slab = msm + (size_t)gm.nkc4 * gm.q * 32;         // [MMA_STAGES][KC][NTP]
+  const MomentsDescK dsc = descs[blockIdx.y];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int M = gm.M, Ds = gm.Ds, O = gm.O, K = gm.K, q = gm.q, KC = gm.KC;
+
+  // weights -> fragment-major, zero padded: Ws[(kc*q + ot)*32 + l] = W[8*ot + (l>>2)][4*kc + (l&3)]
+  for (int idx = threadIdx.x; idx < gm.nkc4 * q * 32; idx += 256) {
+    const int l = idx & 31, f = idx >> 5, ot = f % q, kc = f / q;
+    const int o = 8 * ot + (l >> 2), k = 4 * kc + (l & 3);
+    double v = 0.0;
+    if (o < O && k < K) {
+      if (gm.mode == 0) { const int s = k / Ds, d = k - s * Ds; v = dsc.w[s][(size_t)d * M + o]; }   // ell[d][nm]
+      else { const int s = o / Ds, d = o - s * Ds; v = dsc.w[s][(size_t)d * M + k]; }                // ell_plus[d][nm]
+    }
+    Ws[idx] = v;
+  }
+
+  const long long ntiles = gm.B * gm.ntn;
+  const long long my_tiles = ((long long)blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long nitems = my_tiles * gm.nst;
+
+  // issue the cp.async copies of one slab (item = local tile * nst + slab index)
+  auto issue = [&](long long item) {
+    if (item < nitems) {
+      const long long lt = item / gm.nst;
+      const int st = (int)(item - lt * gm.nst);
+      const long long tile = blockIdx.x + lt * gridDim.x;
+      const long long b = tile / gm.ntn, n0 = (tile - b * gm.ntn) * NT;
+      double *dst = slab + (size_t)(item % MMA_STAGES) * KC * NTP;
+      const int c2 = threadIdx.x % PPR, r0 = threadIdx.x / PPR;
+      const long long n = n0 + 2 * c2;
+      for (int r = r0; r < KC; r += RPP) {
+        const int k = st * KC + r;
+        const bool valid = k < K && n < gm.N;
+        const double *src = dsc.in[0];
+        if (valid) {
+          if (gm.mode == 0) { const int s = k / Ds, d = k - s * Ds; src = dsc.in[s] + b * gm.in_b + (long long)d * gm.in_r + n; }
+          else src = dsc.in[0] + b * gm.in_b + (long long)k * gm.in_r + n;
+        }
+        cp_async16_zfill(dst + (size_t)r * NTP + 2 * c2, src, valid);
+      }
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int s = 0; s < MMA_STAGES - 1; ++s) issue(s);
+
+  double acc[QP][NB][2];
+  const int ncol0 = warp * 8 * NB;  // this warp's first column inside the tile
+
+  for (long long item = 0; item < nitems; ++item) {
+    cp_async_wait<MMA_STAGES - 2>();
+    __syncthreads();  // slab `item` has landed for everyone; slab item-1 is free (also orders the Ws build)
+    issue(item + MMA_STAGES - 1);
+
+    const long long lt = item / gm.nst;
+    const int st = (int)(item - lt * gm.nst);
+    const long long tile = blockIdx.x + lt * gridDim.x;
+    const long long b = tile / gm.ntn, n0 = (tile - b * gm.ntn) * NT;
+    const double *buf = slab + (size_t)(item % MMA_STAGES) * KC * NTP;
+    const int kc_lo = st * (KC / 4);
+    const int kc_hi = min(gm.nkc4, kc_lo + KC / 4);
+
+    for (int pass = 0; pass < gm.npass; ++pass) {
+      if (st == 0 || gm.npass > 1) {
+#pragma unroll
+        for (int a = 0; a < QP; ++a)
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) acc[a][nb][0] = acc[a][nb][1] = 0.0;
+      }
+      const int ot0 = pass * QP;
+      for (int kc = kc_lo; kc < kc_hi; ++kc) {
+        double bf[NB];
+        const double *brow = buf + (size_t)(4 * (kc - kc_lo) + (lane & 3)) * NTP + ncol0 + (lane >> 2);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) bf[nb] = brow[8 * nb];
+        const double *wf = Ws + ((size_t)kc * q + ot0) * 32 + lane;
+#pragma unroll
+        for (int a = 0; a < QP; ++a) {
+          if (ot0 + a < q) {
+            const double af = wf[a * 32];
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) dmma884(acc[a][nb][0], acc[a][nb][1], af, bf[nb]);
+          }
+        }
+      }
+      if (st == gm.nst - 1) {  // epilogue of this pass: C fragment (row = lane>>2, cols 2*(lane&3)+{0,1})
+#pragma unroll
+        for (int a = 0; a < QP; ++a) {
+          const int o = 8 * (ot0 + a) + (lane >> 2);
+          if (ot0 + a < q && o < O) {
+            double *row;
+            if (gm.mode == 0) row = dsc.out[0] + b * gm.out_b + (long long)o * gm.out_r;
+            else { const int s = o / Ds, d = o - s * Ds; row = dsc.out[s] + b * gm.out_b + (long long)d * gm.out_r; }
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+              const long long n = n0 + ncol0 + 8 * nb + 2 * (lane & 3);
+              if (n < gm.N) {
+                double2 v = make_double2(acc[a][nb][0], acc[a][nb][1]);
+                double2 *p = reinterpret_cast<double2 *>(row + n);
+                if (gm.accumulate) { const double2 old = *p; v.x += old.x; v.y += old.y; }
+                *p = v;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+}  // namespace kb200
+
+using namespace kb200;
+
+template <int QP, int NB>
+static int launch_mma(const MomentsDescK *d_views, int n, const MmaGeom &gm, cudaStream_t st) {
+  constexpr int NT = 64 * NB, NTP = NT + 4;
+  const size_t smem = ((size_t)gm.nkc4 * gm.q * 32 + (size_t)MMA_STAGES * gm.KC * NTP) * sizeof(double);
+  if (smem > 200 * 1024) return -1;
+  auto k = moments_mma_kernel<QP, NB>;
+  KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long ntiles = gm.B * gm.ntn;
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2) per_sm = 2;
+  long long ctas = (long long)sm_count() * per_sm / (n > 0 ? n : 1);
+  if (ctas < 1) ctas = 1;
+  if (ctas > ntiles) ctas = ntiles;
+  dim3 grid((unsigned)ctas, n, 1);
+  k<<<grid, 256, smem, st>>>(d_views, gm);
+  return post_launch("moments_mma");
+}
+
+// Returns 0 if handled, -1 if this path does not apply (caller falls back to the DFMA kernels), >0 on error.
+int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, int nsets, int accumulate, const void *d_views,
+                          int n, const void *const *h_ptrs, int n_ptrs, cudaStream_t st) {
+  if (layout != 0 && layout != 1 && layout != 2) return -1;
+  const char *env = getenv("KB200_MOMENTS_DFMA");
+  if (env && env[0] == '1') return -1;
+  for (int i = 0; i < n_ptrs; ++i)
+    if (((uintptr_t)h_ptrs[i] & 15) != 0) return -1;
+  MmaGeom gm;
+  memset(&gm, 0, sizeof(gm));
+  gm.mode = mode; gm.M = M; gm.Ds = Ds; gm.nsets = nsets; gm.accumulate = accumulate;
+  const Strides3 fs = strides_dgz(layout, Ds, Gs, Zs), ms = strides_dgz(layout, M, Gs, Zs);
+  long long flux_b, mom_b;
+  if (layout == 2) { gm.B = Gs; gm.N = Zs; flux_b = fs.g; mom_b = ms.g; }     // GDZ: batch = group
+  else { gm.B = 1; gm.N = (long long)Gs * Zs; flux_b = 0; mom_b = 0; }        // DGZ, DZG
+  if (gm.N % 2 != 0) return -1;
+  if (mode == 0) { gm.O = M; gm.K = nsets * Ds; gm.in_b = flux_b; gm.in_r = fs.a; gm.out_b = mom_b; gm.out_r = ms.a; }
+  else { gm.O = nsets * Ds; gm.K = M; gm.in_b = mom_b; gm.in_r = ms.a; gm.out_b = flux_b; gm.out_r = fs.a; }
+  gm.q = (gm.O + 7) / 8;
+  gm.nkc4 = (gm.K + 3) / 4;
+  const int Kp = gm.nkc4 * 4;
+  // regime: all outputs in registers with K streamed, or K resident with output passes
+  if (gm.q <= 4 || (gm.q <= 13 && Kp > 32)) {
+    gm.KC = Kp < 16 ? Kp : 16;
+    gm.nst = (Kp + gm.KC - 1) / gm.KC;
+    gm.npass = 1;
+    gm.ntn = (gm.N + 127) / 128;
+    if (gm.q <= 4) return launch_mma<4, 2>((const MomentsDescK *)d_views, n, gm, st);
+    return launch_mma<13, 2>((const MomentsDescK *)d_views, n, gm, st);
+  }
+  if (Kp <= 32) {  // K resident
+    gm.KC = Kp; gm.nst = 1; gm.npass = (gm.q + 3) / 4;
+    gm.ntn = (gm.N + 127) / 128;
+    return launch_mma<4, 2>((const MomentsDescK *)d_views, n, gm, st);
+  }
+  if (gm.q <= 16) {  // both large (e.g. Legendre order 9): narrower tiles, all outputs in registers
+    gm.KC = 16; gm.nst = (Kp + 15) / 16; gm.npass = 1;
+    gm.ntn = (gm.N + 63) / 64;
+    return launch_mma<16, 1>((const MomentsDescK *)d_views, n, gm, st);
+  }
+  return -1;
+}

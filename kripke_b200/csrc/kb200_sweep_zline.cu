@@ -43,15 +43,185 @@ __device__ __forceinline__ void stg256(double *p, const double (&v)[4]) {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// everything that is fixed for a thread during the whole launch
+struct ZCtx {
+  const double *rhs_b, *sigt_b;
+  double *psi_b, *ipl, *jpl, *kpl, *iout, *jout, *kout;
+  const double *dx;
+  double2 *fkx, *fjx;
+  const double *cxt, *txc, *cyt, *czt;
+  unsigned row_off, ip_idx, jp_row, kp_row;  // zone part of the line's addresses
+  unsigned sa, sg, Zs;                       // element strides of rhs/psi, zones per subdomain
+  unsigned ipd, ipg, jpd, jpg, kpd, kpg;     // element strides of the three planes
+  int Ds, ni, nb, jw;
+  int d0, g0, dstep, gstep;                  // first element of the stream and the stream stride
+  int T, Hend, jjkk;
+  bool line_ok, i_zero, j_zero, k_zero, j_first, k_first, j_last, k_last, uniform_x;
+};
+
+template <bool EXACT, bool FWD>
+__device__ __forceinline__ void zline_run(const ZCtx &cx_) {
+  const ZCtx c_ = cx_;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nb = c_.nb, ni = c_.ni;
+  int c = nb - 1;
+  int d = 0, g = 0, dN = c_.d0, gN = c_.g0;
+  unsigned eoff = 0, soff = 0;
+  double cx = 0, cy = 0, cz = 0, csum = 0;
+  double r4n[4] = {0, 0, 0, 0}, s4n[4] = {1, 1, 1, 1}, finn = 0.0;
+  double fi = 0.0;
+  double oj[4] = {0, 0, 0, 0};
+  int t = -1 - c_.jjkk;
+  constexpr int XS = (ZW + 1) * 32;  // slots per half-buffer of the k exchange
+  constexpr int JS = ZW * 32;
+
+  for (int H = -1; H < c_.Hend; ++H, ++t) {  // H = -1 only prefetches the first block of line (0,0)
+    const bool act = c_.line_ok && (unsigned)t < (unsigned)c_.T;
+    const bool pre = c_.line_ok && (unsigned)(t + 1) < (unsigned)c_.T;
+    const int par = H & 1;
+
+    double r4[4], s4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { r4[u] = r4n[u]; s4[u] = s4n[u]; }
+    const double fin = finn;
+
+    if (act) {
+      if (++c == nb) {  // next element of the stream
+        c = 0;
+        d = dN; g = gN;
+        dN = d + c_.dstep; gN = g + c_.gstep;
+        if (dN >= c_.Ds) { dN -= c_.Ds; ++gN; }
+        eoff = (unsigned)d * c_.sa + (unsigned)g * c_.sg;
+        soff = (unsigned)g * c_.Zs;
+        cx = c_.cxt[d]; cy = c_.cyt[d * 32 + lane]; cz = c_.czt[d * ZW + warp];
+        csum = __dadd_rn(__dadd_rn(cx, cy), cz);
+      }
+    }
+
+    // ---- prefetch block t+1 (registers for rhs/sigt, cp.async into the exchange slots for boundary faces) ----
+    if (pre) {
+      int cn = c + 1, dn = d, gn = g;
+      unsigned eoffn = eoff, soffn = soff;
+      if (!act || cn == nb) {
+        cn = 0; dn = dN; gn = gN;
+        eoffn = (unsigned)dn * c_.sa + (unsigned)gn * c_.sg;
+        soffn = (unsigned)gn * c_.Zs;
+        finn = c_.i_zero ? 0.0 : c_.ipl[(unsigned)dn * c_.ipd + (unsigned)gn * c_.ipg + c_.ip_idx];
+      }
+      const unsigned i0n = FWD ? 4u * cn : (unsigned)(ni - 4 - 4 * cn);
+      ldg256_nc(c_.rhs_b + (eoffn + c_.row_off + i0n), r4n);
+      ldg256_nc(c_.sigt_b + (soffn + c_.row_off + i0n), s4n);
+      if (c_.j_first && !c_.j_zero) {
+        const double *src = c_.jpl + ((unsigned)dn * c_.jpd + (unsigned)gn * c_.jpg + c_.jp_row + i0n);
+        cp_async16(c_.fjx + par * (2 * JS) + threadIdx.x, src);
+        cp_async16(c_.fjx + par * (2 * JS) + JS + threadIdx.x, src + 2);
+      }
+      if (c_.k_first && !c_.k_zero) {
+        const double *src = c_.kpl + ((unsigned)dn * c_.kpd + (unsigned)gn * c_.kpg + c_.kp_row + i0n);
+        cp_async16(c_.fkx + par * (2 * XS) + warp * 32 + lane, src);
+        cp_async16(c_.fkx + par * (2 * XS) + XS + warp * 32 + lane, src + 2);
+      }
+    }
+
+    // ---- incoming faces of block t: j from the previous lane (shuffle) or the tile boundary slot,
+    //      k from the previous warp's slot (tile boundary: filled by cp.async one macro-step ago) ----
+    double fj[4], fk[4];
+    {
+      double sj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sj[u] = __shfl_up_sync(0xffffffffu, oj[u], 1, c_.jw);
+      if (c_.j_first) {
+        if (c_.j_zero) { fj[0] = fj[1] = fj[2] = fj[3] = 0.0; }
+        else {
+          const double2 a = c_.fjx[(par ^ 1) * (2 * JS) + threadIdx.x], b = c_.fjx[(par ^ 1) * (2 * JS) + JS + threadIdx.x];
+          fj[0] = a.x; fj[1] = a.y; fj[2] = b.x; fj[3] = b.y;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) fj[u] = sj[u];
+      }
+      if (c_.k_first && c_.k_zero) { fk[0] = fk[1] = fk[2] = fk[3] = 0.0; }
+      else {
+        const double2 a = c_.fkx[(par ^ 1) * (2 * XS) + warp * 32 + lane], b = c_.fkx[(par ^ 1) * (2 * XS) + XS + warp * 32 + lane];
+        fk[0] = a.x; fk[1] = a.y; fk[2] = b.x; fk[3] = b.y;
+      }
+    }
+
+    if (act) {
+      if (c == 0) fi = fin;
+      const unsigned i0 = FWD ? 4u * c : (unsigned)(ni - 4 - 4 * c);
+      double p4[4], ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int m = FWD ? u : 3 - u;  // memory slot of the u-th zone in sweep order
+        double cxu = cx, cs = csum;
+        if (!c_.uniform_x) {
+          cxu = __ddiv_rn(c_.txc[d], c_.dx[i0 + m]);
+          cs = __dadd_rn(__dadd_rn(cxu, cy), cz);
+        }
+        const double den = __dadd_rn(cs, s4[m]);
+        double p;
+        if (EXACT) {
+          double num = __dadd_rn(r4[m], __dmul_rn(fi, cxu));
+          num = __dadd_rn(num, __dmul_rn(fj[m], cy));
+          num = __dadd_rn(num, __dmul_rn(fk[m], cz));
+          p = __ddiv_rn(num, den);
+        } else {
+          const double rc = __drcp_rn(den);
+          const double part = fma(fk[m], cz, fma(fj[m], cy, r4[m]));
+          const double num = fma(fi, cxu, part);
+          const double q = num * rc;
+          const double rem = fma(-den, q, num);
+          p = fma(rem, rc, q);
+        }
+        const double p2 = 2.0 * p;
+        fi = p2 - fi;
+        p4[m] = p; oj[m] = p2 - fj[m]; ok[m] = p2 - fk[m];
+      }
+      stg256(c_.psi_b + (eoff + c_.row_off + i0), p4);
+      if (c == nb - 1) {
+        const unsigned ix = (unsigned)d * c_.ipd + (unsigned)g * c_.ipg + c_.ip_idx;
+        c_.ipl[ix] = fi;
+        if (c_.iout) c_.iout[ix] = fi;
+      }
+      if (c_.j_last) {
+        const unsigned ix = (unsigned)d * c_.jpd + (unsigned)g * c_.jpg + c_.jp_row + i0;
+        stg256(c_.jpl + ix, oj);
+        if (c_.jout) stg256(c_.jout + ix, oj);
+      }
+      if (c_.k_last) {
+        const unsigned ix = (unsigned)d * c_.kpd + (unsigned)g * c_.kpg + c_.kp_row + i0;
+        stg256(c_.kpl + ix, ok);
+        if (c_.kout) stg256(c_.kout + ix, ok);
+      } else {
+        c_.fkx[par * (2 * XS) + (warp + 1) * 32 + lane] = make_double2(ok[0], ok[1]);
+        c_.fkx[par * (2 * XS) + XS + (warp + 1) * 32 + lane] = make_double2(ok[2], ok[3]);
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+  }
+}
+
 template <bool EXACT>
 __global__ void __launch_bounds__(ZW * 32, 1) sweep_zline_kernel(const kb200_sweep_desc *__restrict__ descs, ZGeom gm) {
   extern __shared__ __align__(16) unsigned char zsm[];
-  // shared memory: k-face exchange [2 buffers][2 halves][ZW*32] double2, then the per-direction tables
-  double2 *fkx = reinterpret_cast<double2 *>(zsm);
-  double *cxt = reinterpret_cast<double *>(zsm + (size_t)2 * 2 * ZW * 32 * sizeof(double2));  // [Ds]   2*xcos/dx[0]
-  double *txc = cxt + gm.Ds;                                                                  // [Ds]   2*xcos
-  double *cyt = txc + gm.Ds;                                                                  // [Ds][32]
-  double *czt = cyt + (size_t)gm.Ds * 32;                                                     // [Ds][ZW]
+  // shared memory: k-face exchange [2 buffers][2 halves][(ZW+1)*32] double2, j-boundary staging
+  // [2][2][ZW*32] double2, then the per-direction coefficient tables
+  ZCtx c;
+  c.fkx = reinterpret_cast<double2 *>(zsm);
+  c.fjx = c.fkx + 2 * 2 * (ZW + 1) * 32;
+  double *cxt = reinterpret_cast<double *>(c.fjx + 2 * 2 * ZW * 32);  // [Ds]   2*xcos/dx[0]
+  double *txc = cxt + gm.Ds;                                           // [Ds]   2*xcos
+  double *cyt = txc + gm.Ds;                                           // [Ds][32]
+  double *czt = cyt + (size_t)gm.Ds * 32;                              // [Ds][ZW]
+  c.cxt = cxt; c.txc = txc; c.cyt = cyt; c.czt = czt;
 
   const kb200_sweep_desc &ds = descs[blockIdx.z];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -68,8 +238,8 @@ __global__ void __launch_bounds__(ZW * 32, 1) sweep_zline_kernel(const kb200_swe
   const int tj_lo = max(0, gm.diag - (gm.ntk - 1));
   const int tj = tj_lo + blockIdx.y, tk = gm.diag - tj;
   const int tjn = min(jw, nj - tj * jw), tkn = min(kw, nk - tk * kw);
-  const bool line_ok = jj < tjn && kk < tkn;
-  const int id = ds.id, jd = ds.jd, kd = ds.kd;
+  c.line_ok = jj < tjn && kk < tkn;
+  const int jd = ds.jd, kd = ds.kd;
   const int jl = tj * jw + min(jj, tjn - 1), kl = tk * kw + min(kk, tkn - 1);
   const int jz = (jd > 0) ? jl : nj - 1 - jl, kz = (kd > 0) ? kl : nk - 1 - kl;
 
@@ -78,23 +248,27 @@ __global__ void __launch_bounds__(ZW * 32, 1) sweep_zline_kernel(const kb200_swe
   const StridesP ips = strides_plane(gm.layout, Ds, gm.Gs, nj, nk);
   const StridesP jps = strides_plane(gm.layout, Ds, gm.Gs, ni, nk);
   const StridesP kps = strides_plane(gm.layout, Ds, gm.Gs, ni, nj);
-  const long long row_off = ((long long)kz * nj + jz) * ni;  // first zone of this line
-  const long long ip_idx = (long long)jz + (long long)kz * nj;  // i_plane [k][j]
-  const long long jp_row = (long long)kz * ni;                  // j_plane [k][i]
-  const long long kp_row = (long long)jz * ni;                  // k_plane [j][i]
+  c.row_off = (unsigned)(((long long)kz * nj + jz) * ni);  // first zone of this line
+  c.ip_idx = (unsigned)(jz + kz * nj);                     // i_plane [k][j]
+  c.jp_row = (unsigned)(kz * ni);                          // j_plane [k][i]
+  c.kp_row = (unsigned)(jz * ni);                          // k_plane [j][i]
+  c.sa = (unsigned)fs.a; c.sg = (unsigned)fs.g; c.Zs = (unsigned)Zs;
+  c.ipd = (unsigned)ips.d; c.ipg = (unsigned)ips.g;
+  c.jpd = (unsigned)jps.d; c.jpg = (unsigned)jps.g;
+  c.kpd = (unsigned)kps.d; c.kpg = (unsigned)kps.g;
+  c.Ds = Ds; c.ni = ni; c.nb = nb; c.jw = jw;
 
-  const bool i_zero = ds.inflow_zero[0] != 0;
-  const bool j_zero = ds.inflow_zero[1] != 0 && tj == 0;
-  const bool k_zero = ds.inflow_zero[2] != 0 && tk == 0;
-  const bool j_first = jj == 0, k_first = kk == 0;
-  const bool j_last = jj == tjn - 1, k_last = kk == tkn - 1;
-  double *__restrict__ iout = ds.out_plane[0];
-  double *__restrict__ jout = (tj == gm.ntj - 1) ? ds.out_plane[1] : nullptr;
-  double *__restrict__ kout = (tk == gm.ntk - 1) ? ds.out_plane[2] : nullptr;
-  const double *__restrict__ rhs_b = ds.rhs;
-  const double *__restrict__ sigt_b = ds.sigt;
-  double *__restrict__ psi_b = ds.psi;
-  double *ipl = ds.i_plane, *jpl = ds.j_plane, *kpl = ds.k_plane;
+  c.i_zero = ds.inflow_zero[0] != 0;
+  c.j_zero = ds.inflow_zero[1] != 0 && tj == 0;
+  c.k_zero = ds.inflow_zero[2] != 0 && tk == 0;
+  c.j_first = jj == 0; c.k_first = kk == 0;
+  c.j_last = jj == tjn - 1; c.k_last = kk == tkn - 1;
+  c.iout = ds.out_plane[0];
+  c.jout = (tj == gm.ntj - 1) ? ds.out_plane[1] : nullptr;
+  c.kout = (tk == gm.ntk - 1) ? ds.out_plane[2] : nullptr;
+  c.rhs_b = ds.rhs; c.sigt_b = ds.sigt; c.psi_b = ds.psi;
+  c.ipl = ds.i_plane; c.jpl = ds.j_plane; c.kpl = ds.k_plane;
+  c.dx = ds.dx;
 
   // per-direction coefficient tables (2*cos/delta, SweepSubdomain.cpp:88-93)
   for (int d = threadIdx.x; d < Ds; d += blockDim.x) {
@@ -116,148 +290,20 @@ __global__ void __launch_bounds__(ZW * 32, 1) sweep_zline_kernel(const kb200_swe
   }
   int uni = 1;
   for (int i = threadIdx.x; i < ni; i += blockDim.x) uni &= (ds.dx[i] == ds.dx[0]);
-  const bool uniform_x = __syncthreads_and(uni) != 0;  // also orders the table writes
+  c.uniform_x = __syncthreads_and(uni) != 0;  // also orders the table writes
 
-  // stream bookkeeping
+  // stream bookkeeping: this thread's line works on elements stream, stream+S, ...
   const int cnt = (stream < E) ? (E - stream + nstreams - 1) / nstreams : 0;
-  const int T = cnt * nb;
+  c.T = cnt * nb;
   const int stream0 = blockIdx.x * spw;  // the longest stream of this CTA
   const int cnt0 = (stream0 < E) ? (E - stream0 + nstreams - 1) / nstreams : 0;
-  const int Hend = cnt0 * nb + (tjn - 1) + (tkn - 1);
+  c.Hend = cnt0 * nb + (tjn - 1) + (tkn - 1);
+  c.jjkk = jj + kk;
+  c.g0 = stream / Ds; c.d0 = stream - c.g0 * Ds;
+  c.gstep = nstreams / Ds; c.dstep = nstreams - c.gstep * Ds;
 
-  // element state of the block being computed
-  int c = nb - 1, e = stream - nstreams;
-  long long off = 0, sgo = 0, ipo = 0, jpo = 0, kpo = 0;
-  double cx = 0, cy = 0, cz = 0, csum = 0, tx = 0;
-  // prefetched operands of the next block
-  double r4n[4] = {0, 0, 0, 0}, s4n[4] = {1, 1, 1, 1}, fjbn[4] = {0, 0, 0, 0}, fkbn[4] = {0, 0, 0, 0}, finn = 0.0;
-  double fi = 0.0;
-  double oj[4] = {0, 0, 0, 0};
-
-  auto elem_offsets = [&](int en, long long &o, long long &sg, long long &ip, long long &jp, long long &kp) {
-    const int g = en / Ds, d = en - g * Ds;
-    o = (long long)d * fs.a + (long long)g * fs.g;
-    sg = (long long)g * Zs;
-    ip = (long long)d * ips.d + (long long)g * ips.g;
-    jp = (long long)d * jps.d + (long long)g * jps.g;
-    kp = (long long)d * kps.d + (long long)g * kps.g;
-  };
-
-  for (int H = -1; H < Hend; ++H) {  // H = -1 only prefetches the first block of line (0,0)
-    const int t = H - jj - kk;
-    const bool act = line_ok && t >= 0 && t < T;
-    const bool pre = line_ok && t + 1 >= 0 && t + 1 < T;
-
-    // operands loaded during the previous macro-step
-    double r4[4], s4[4], fjb[4], fkb[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { r4[u] = r4n[u]; s4[u] = s4n[u]; fjb[u] = fjbn[u]; fkb[u] = fkbn[u]; }
-    const double fin = finn;
-
-    if (act) {
-      if (++c == nb) {  // next element of the stream
-        c = 0;
-        e += nstreams;
-        elem_offsets(e, off, sgo, ipo, jpo, kpo);
-        const int d = e % Ds;
-        cx = cxt[d]; tx = txc[d]; cy = cyt[d * 32 + lane]; cz = czt[d * ZW + warp];
-        csum = __dadd_rn(__dadd_rn(cx, cy), cz);
-      }
-    }
-
-    // ---- prefetch block t+1 ----
-    if (pre) {
-      int cn = c + 1;
-      long long offn = off, sgn = sgo, ipn = ipo, jpn = jpo, kpn = kpo;
-      if (!act || cn == nb) {
-        cn = 0;
-        elem_offsets(act ? e + nstreams : stream, offn, sgn, ipn, jpn, kpn);
-        finn = i_zero ? 0.0 : ipl[ipn + ip_idx];
-      }
-      const int i0n = (id > 0) ? 4 * cn : ni - 4 - 4 * cn;
-      ldg256_nc(rhs_b + offn + row_off + i0n, r4n);
-      ldg256_nc(sigt_b + sgn + row_off + i0n, s4n);
-      if (j_first && !j_zero) ldg256(jpl + jpn + jp_row + i0n, fjbn);
-      if (k_first && !k_zero) ldg256(kpl + kpn + kp_row + i0n, fkbn);
-    }
-
-    // ---- incoming j faces: previous lane's outgoing faces of the previous macro-step ----
-    double fj[4], fk[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const double v = __shfl_up_sync(0xffffffffu, oj[u], 1, jw);
-      fj[u] = j_first ? (j_zero ? 0.0 : fjb[u]) : v;
-    }
-    // ---- incoming k faces: previous warp's outgoing faces of the previous macro-step ----
-    {
-      const double2 *rd = fkx + (size_t)((H & 1) ^ 1) * (2 * ZW * 32);
-      if (k_first) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) fk[u] = k_zero ? 0.0 : fkb[u];
-      } else {
-        const double2 a = rd[(warp - 1) * 32 + lane], b = rd[ZW * 32 + (warp - 1) * 32 + lane];
-        fk[0] = a.x; fk[1] = a.y; fk[2] = b.x; fk[3] = b.y;
-      }
-    }
-
-    if (act) {
-      if (c == 0) fi = fin;
-      const int i0 = (id > 0) ? 4 * c : ni - 4 - 4 * c;
-      double p4[4], ok[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int m = (id > 0) ? u : 3 - u;  // memory slot of the u-th zone in sweep order
-        // select without dynamic register indexing
-        const double r = (id > 0) ? r4[u] : r4[3 - u];
-        const double st = (id > 0) ? s4[u] : s4[3 - u];
-        const double fju = (id > 0) ? fj[u] : fj[3 - u];
-        const double fku = (id > 0) ? fk[u] : fk[3 - u];
-        double cxu = cx, cs = csum;
-        if (!uniform_x) {
-          cxu = __ddiv_rn(tx, ds.dx[i0 + m]);
-          cs = __dadd_rn(__dadd_rn(cxu, cy), cz);
-        }
-        const double den = __dadd_rn(cs, st);
-        double p;
-        if (EXACT) {
-          double num = __dadd_rn(r, __dmul_rn(fi, cxu));
-          num = __dadd_rn(num, __dmul_rn(fju, cy));
-          num = __dadd_rn(num, __dmul_rn(fku, cz));
-          p = __ddiv_rn(num, den);
-        } else {
-          const double rc = __drcp_rn(den);
-          const double part = fma(fku, cz, fma(fju, cy, r));
-          const double num = fma(fi, cxu, part);
-          const double q = num * rc;
-          const double rem = fma(-den, q, num);
-          p = fma(rem, rc, q);
-        }
-        const double p2 = 2.0 * p;
-        fi = p2 - fi;
-        const double ojv = p2 - fju, okv = p2 - fku;
-        if (id > 0) { p4[u] = p; oj[u] = ojv; ok[u] = okv; }
-        else { p4[3 - u] = p; oj[3 - u] = ojv; ok[3 - u] = okv; }
-      }
-      stg256(psi_b + off + row_off + i0, p4);
-      if (c == nb - 1) {
-        ipl[ipo + ip_idx] = fi;
-        if (iout) iout[ipo + ip_idx] = fi;
-      }
-      if (j_last) {
-        stg256(jpl + jpo + jp_row + i0, oj);
-        if (jout) stg256(jout + jpo + jp_row + i0, oj);
-      }
-      if (k_last) {
-        stg256(kpl + kpo + kp_row + i0, ok);
-        if (kout) stg256(kout + kpo + kp_row + i0, ok);
-      } else {
-        double2 *wr = fkx + (size_t)(H & 1) * (2 * ZW * 32);
-        wr[warp * 32 + lane] = make_double2(ok[0], ok[1]);
-        wr[ZW * 32 + warp * 32 + lane] = make_double2(ok[2], ok[3]);
-      }
-    }
-    __syncthreads();
-  }
+  if (ds.id > 0) zline_run<EXACT, true>(c);
+  else zline_run<EXACT, false>(c);
 }
 
 }  // namespace kb200
@@ -289,7 +335,9 @@ int kb200_sweep_zline_try(const kb200_sweep_desc *h, int n, const void *d_descs,
   gm.kw = pow2_ceil(gm.nk, ZW);
   gm.ntj = (gm.nj + gm.jw - 1) / gm.jw;
   gm.ntk = (gm.nk + gm.kw - 1) / gm.kw;
-  const size_t smem = (size_t)2 * 2 * ZW * 32 * sizeof(double2) + (size_t)gm.Ds * (2 + 32 + ZW) * sizeof(double);
+  const size_t smem = (size_t)2 * 2 * ((ZW + 1) * 32 + ZW * 32) * sizeof(double2) + (size_t)gm.Ds * (2 + 32 + ZW) * sizeof(double);
+  // the kernel indexes every chunk with 32-bit element offsets
+  if ((double)gm.Ds * gm.Gs * gm.ni * gm.nj * gm.nk >= 2147483648.0) return -1;
   if (smem > 200 * 1024) return -1;
   auto kern = exact_mode() ? sweep_zline_kernel<true> : sweep_zline_kernel<false>;
   KB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
