@@ -84,52 +84,68 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
     Ws[idx] = v;
   }
 
+  // all loop control is 32-bit and incremental (no divisions inside the pipeline)
+  const int ntn = (int)gm.ntn, nst = gm.nst;
   const long long ntiles = gm.B * gm.ntn;
-  const long long my_tiles = ((long long)blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const long long nitems = my_tiles * gm.nst;
+  const int my_tiles = ((long long)blockIdx.x < ntiles) ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const int nitems = my_tiles * nst;
 
-  // issue the cp.async copies of one slab (item = local tile * nst + slab index)
-  auto issue = [&](long long item) {
-    if (item < nitems) {
-      const long long lt = item / gm.nst;
-      const int st = (int)(item - lt * gm.nst);
-      const long long tile = blockIdx.x + lt * gridDim.x;
-      const long long b = tile / gm.ntn, n0 = (tile - b * gm.ntn) * NT;
-      double *dst = slab + (size_t)(item % MMA_STAGES) * KC * NTP;
-      const int c2 = threadIdx.x % PPR, r0 = threadIdx.x / PPR;
-      const long long n = n0 + 2 * c2;
+  // producer cursor: next slab to fetch
+  int i_left = nitems, i_st = 0, i_tn = (int)(blockIdx.x % gm.ntn), i_b = (int)(blockIdx.x / gm.ntn), i_buf = 0;
+  int i_s0 = 0, i_d0 = 0;  // (direction set, direction) of the slab's first row (LTimes)
+  const int c2 = threadIdx.x % PPR, r0 = threadIdx.x / PPR;
+  auto issue = [&]() {
+    if (i_left > 0) {
+      double *dst = slab + (size_t)i_buf * KC * NTP + 2 * c2;
+      const long long n = (long long)i_tn * NT + 2 * c2;
+      const bool ncol = n < gm.N;
+      const long long boff = (long long)i_b * gm.in_b + n;
       for (int r = r0; r < KC; r += RPP) {
-        const int k = st * KC + r;
-        const bool valid = k < K && n < gm.N;
+        bool valid = ncol;
         const double *src = dsc.in[0];
-        if (valid) {
-          if (gm.mode == 0) { const int s = k / Ds, d = k - s * Ds; src = dsc.in[s] + b * gm.in_b + (long long)d * gm.in_r + n; }
-          else src = dsc.in[0] + b * gm.in_b + (long long)k * gm.in_r + n;
+        if (gm.mode == 0) {
+          int d = i_d0 + r, sset = i_s0;
+          while (d >= Ds) { d -= Ds; ++sset; }
+          valid = valid && sset < gm.nsets;
+          if (valid) src = dsc.in[sset] + (boff + (long long)d * gm.in_r);
+        } else {
+          const int k = i_st * KC + r;
+          valid = valid && k < K;
+          if (valid) src += boff + (long long)k * gm.in_r;
         }
-        cp_async16_zfill(dst + (size_t)r * NTP + 2 * c2, src, valid);
+        cp_async16_zfill(dst + (size_t)r * NTP, src, valid);
+      }
+      --i_left;
+      if (++i_st == nst) {
+        i_st = 0; i_s0 = 0; i_d0 = 0;
+        i_tn += gridDim.x;
+        while (i_tn >= ntn) { i_tn -= ntn; ++i_b; }
+      } else {
+        i_d0 += KC;
+        while (i_d0 >= Ds) { i_d0 -= Ds; ++i_s0; }
       }
     }
     cp_async_commit();
+    if (++i_buf == MMA_STAGES) i_buf = 0;
   };
 
 #pragma unroll
-  for (int s = 0; s < MMA_STAGES - 1; ++s) issue(s);
+  for (int s = 0; s < MMA_STAGES - 1; ++s) issue();
 
   double acc[QP][NB][2];
   const int ncol0 = warp * 8 * NB;  // this warp's first column inside the tile
+  // consumer cursor
+  int st = 0, tn = (int)(blockIdx.x % gm.ntn), b = (int)(blockIdx.x / gm.ntn), cbuf = 0;
 
-  for (long long item = 0; item < nitems; ++item) {
+  for (int item = 0; item < nitems; ++item) {
     cp_async_wait<MMA_STAGES - 2>();
     __syncthreads();  // slab `item` has landed for everyone; slab item-1 is free (also orders the Ws build)
-    issue(item + MMA_STAGES - 1);
+    issue();
 
-    const long long lt = item / gm.nst;
-    const int st = (int)(item - lt * gm.nst);
-    const long long tile = blockIdx.x + lt * gridDim.x;
-    const long long b = tile / gm.ntn, n0 = (tile - b * gm.ntn) * NT;
-    const double *buf = slab + (size_t)(item % MMA_STAGES) * KC * NTP;
+    const double *buf = slab + (size_t)cbuf * KC * NTP;
     const int kc_lo = st * (KC / 4);
-    const int kc_hi = min(gm.nkc4, kc_lo + KC / 4);
+    const int nkc = min(gm.nkc4 - kc_lo, KC / 4);
+    const double *bbase = buf + (size_t)(lane & 3) * NTP + ncol0 + (lane >> 2);
 
     for (int pass = 0; pass < gm.npass; ++pass) {
       if (st == 0 || gm.npass > 1) {
@@ -139,32 +155,48 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
           for (int nb = 0; nb < NB; ++nb) acc[a][nb][0] = acc[a][nb][1] = 0.0;
       }
       const int ot0 = pass * QP;
-      for (int kc = kc_lo; kc < kc_hi; ++kc) {
-        double bf[NB];
-        const double *brow = buf + (size_t)(4 * (kc - kc_lo) + (lane & 3)) * NTP + ncol0 + (lane >> 2);
+      const double *wf = Ws + ((size_t)kc_lo * q + ot0) * 32 + lane;
+      const double *brow = bbase;
+      if (ot0 + QP <= q) {  // full pass: no per-tile predicates
+#pragma unroll 2
+        for (int kc = 0; kc < nkc; ++kc, brow += 4 * NTP, wf += q * 32) {
+          double bf[NB], af[QP];
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) bf[nb] = brow[8 * nb];
-        const double *wf = Ws + ((size_t)kc * q + ot0) * 32 + lane;
+          for (int nb = 0; nb < NB; ++nb) bf[nb] = brow[8 * nb];
 #pragma unroll
-        for (int a = 0; a < QP; ++a) {
-          if (ot0 + a < q) {
-            const double af = wf[a * 32];
+          for (int a = 0; a < QP; ++a) af[a] = wf[a * 32];
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) dmma884(acc[a][nb][0], acc[a][nb][1], af, bf[nb]);
+          for (int a = 0; a < QP; ++a)
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) dmma884(acc[a][nb][0], acc[a][nb][1], af[a], bf[nb]);
+        }
+      } else {
+        for (int kc = 0; kc < nkc; ++kc, brow += 4 * NTP, wf += q * 32) {
+          double bf[NB];
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) bf[nb] = brow[8 * nb];
+#pragma unroll
+          for (int a = 0; a < QP; ++a) {
+            if (ot0 + a < q) {
+              const double af = wf[a * 32];
+#pragma unroll
+              for (int nb = 0; nb < NB; ++nb) dmma884(acc[a][nb][0], acc[a][nb][1], af, bf[nb]);
+            }
           }
         }
       }
-      if (st == gm.nst - 1) {  // epilogue of this pass: C fragment (row = lane>>2, cols 2*(lane&3)+{0,1})
+      if (st == nst - 1) {  // epilogue of this pass: C fragment (row = lane>>2, cols 2*(lane&3)+{0,1})
+        const long long ncol = (long long)tn * NT + ncol0 + 2 * (lane & 3);
 #pragma unroll
         for (int a = 0; a < QP; ++a) {
           const int o = 8 * (ot0 + a) + (lane >> 2);
           if (ot0 + a < q && o < O) {
             double *row;
-            if (gm.mode == 0) row = dsc.out[0] + b * gm.out_b + (long long)o * gm.out_r;
-            else { const int s = o / Ds, d = o - s * Ds; row = dsc.out[s] + b * gm.out_b + (long long)d * gm.out_r; }
+            if (gm.mode == 0) row = dsc.out[0] + ((long long)b * gm.out_b + (long long)o * gm.out_r);
+            else { const int sset = o / Ds, d = o - sset * Ds; row = dsc.out[sset] + ((long long)b * gm.out_b + (long long)d * gm.out_r); }
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) {
-              const long long n = n0 + ncol0 + 8 * nb + 2 * (lane & 3);
+              const long long n = ncol + 8 * nb;
               if (n < gm.N) {
                 double2 v = make_double2(acc[a][nb][0], acc[a][nb][1]);
                 double2 *p = reinterpret_cast<double2 *>(row + n);
@@ -175,6 +207,12 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
           }
         }
       }
+    }
+    if (++cbuf == MMA_STAGES) cbuf = 0;
+    if (++st == nst) {
+      st = 0;
+      tn += gridDim.x;
+      while (tn >= ntn) { tn -= ntn; ++b; }
     }
   }
   cp_async_wait<0>();

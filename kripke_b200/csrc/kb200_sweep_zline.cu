@@ -30,6 +30,7 @@ struct ZGeom {
   int layout, Ds, Gs, ni, nj, nk, nb;
   int ntj, ntk, diag;
   int jw, kw;  // lanes per j-group / warps per k-group (powers of two)
+  int exp;     // timing experiments (KB200_ZEXP bitmask; results are wrong when non-zero)
 };
 
 __device__ __forceinline__ void ldg256_nc(const double *p, double (&v)[4]) {
@@ -47,6 +48,9 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // everything that is fixed for a thread during the whole launch
@@ -54,7 +58,7 @@ struct ZCtx {
   const double *rhs_b, *sigt_b;
   double *psi_b, *ipl, *jpl, *kpl, *iout, *jout, *kout;
   const double *dx;
-  double2 *fkx, *fjx;
+  double2 *fkx, *fjx, *fkin;
   const double *cxt, *txc, *cyt, *czt;
   unsigned row_off, ip_idx, jp_row, kp_row;  // zone part of the line's addresses
   unsigned sa, sg, Zs;                       // element strides of rhs/psi, zones per subdomain
@@ -63,6 +67,7 @@ struct ZCtx {
   int d0, g0, dstep, gstep;                  // first element of the stream and the stream stride
   int T, Hend, jjkk;
   bool line_ok, i_zero, j_zero, k_zero, j_first, k_first, j_last, k_last, uniform_x;
+  int exp;
 };
 
 template <bool EXACT, bool FWD>
@@ -77,11 +82,14 @@ __device__ __forceinline__ void zline_run(const ZCtx &cx_) {
   double r4n[4] = {0, 0, 0, 0}, s4n[4] = {1, 1, 1, 1}, finn = 0.0;
   double fi = 0.0;
   double oj[4] = {0, 0, 0, 0};
-  int t = -1 - c_.jjkk;
   constexpr int XS = (ZW + 1) * 32;  // slots per half-buffer of the k exchange
-  constexpr int JS = ZW * 32;
+  constexpr int JS = ZW * 32;        // slots per half-buffer of the boundary staging rings
+  // boundary-face cursor: the block this line will compute two macro-steps from now
+  int cF = 0, dF = c_.d0, gF = c_.g0;
+  int ring = 0;  // (H + 2) mod 3
 
-  for (int H = -1; H < c_.Hend; ++H, ++t) {  // H = -1 only prefetches the first block of line (0,0)
+  int t = -2 - c_.jjkk;
+  for (int H = -2; H < c_.Hend; ++H, ++t) {  // H < 0 only prefetches the first blocks of line (0,0)
     const bool act = c_.line_ok && (unsigned)t < (unsigned)c_.T;
     const bool pre = c_.line_ok && (unsigned)(t + 1) < (unsigned)c_.T;
     const int par = H & 1;
@@ -115,19 +123,31 @@ __device__ __forceinline__ void zline_run(const ZCtx &cx_) {
         finn = c_.i_zero ? 0.0 : c_.ipl[(unsigned)dn * c_.ipd + (unsigned)gn * c_.ipg + c_.ip_idx];
       }
       const unsigned i0n = FWD ? 4u * cn : (unsigned)(ni - 4 - 4 * cn);
-      ldg256_nc(c_.rhs_b + (eoffn + c_.row_off + i0n), r4n);
-      ldg256_nc(c_.sigt_b + (soffn + c_.row_off + i0n), s4n);
+      if (!(c_.exp & 4)) ldg256_nc(c_.rhs_b + (eoffn + c_.row_off + i0n), r4n);
+      if (!(c_.exp & 1)) ldg256_nc(c_.sigt_b + (soffn + c_.row_off + i0n), s4n);
+    }
+
+    // ---- tile-boundary faces of block t+2: cp.async into a 3-slot ring (waited for one macro-step later) ----
+    if (c_.line_ok && (unsigned)(t + 2) < (unsigned)c_.T) {
+      const unsigned i0f = FWD ? 4u * cF : (unsigned)(ni - 4 - 4 * cF);
       if (c_.j_first && !c_.j_zero) {
-        const double *src = c_.jpl + ((unsigned)dn * c_.jpd + (unsigned)gn * c_.jpg + c_.jp_row + i0n);
-        cp_async16(c_.fjx + par * (2 * JS) + threadIdx.x, src);
-        cp_async16(c_.fjx + par * (2 * JS) + JS + threadIdx.x, src + 2);
+        const double *src = c_.jpl + ((unsigned)dF * c_.jpd + (unsigned)gF * c_.jpg + c_.jp_row + i0f);
+        cp_async16(c_.fjx + ring * (2 * JS) + threadIdx.x, src);
+        cp_async16(c_.fjx + ring * (2 * JS) + JS + threadIdx.x, src + 2);
       }
       if (c_.k_first && !c_.k_zero) {
-        const double *src = c_.kpl + ((unsigned)dn * c_.kpd + (unsigned)gn * c_.kpg + c_.kp_row + i0n);
-        cp_async16(c_.fkx + par * (2 * XS) + warp * 32 + lane, src);
-        cp_async16(c_.fkx + par * (2 * XS) + XS + warp * 32 + lane, src + 2);
+        const double *src = c_.kpl + ((unsigned)dF * c_.kpd + (unsigned)gF * c_.kpg + c_.kp_row + i0f);
+        cp_async16(c_.fkin + ring * (2 * JS) + threadIdx.x, src);
+        cp_async16(c_.fkin + ring * (2 * JS) + JS + threadIdx.x, src + 2);
+      }
+      if (++cF == nb) {
+        cF = 0;
+        dF += c_.dstep; gF += c_.gstep;
+        if (dF >= c_.Ds) { dF -= c_.Ds; ++gF; }
       }
     }
+    cp_async_commit();
+    const int rcur = (ring == 2) ? 0 : ring + 1;  // H mod 3: the slot fetched two macro-steps ago
 
     // ---- incoming faces of block t: j from the previous lane (shuffle) or the tile boundary slot,
     //      k from the previous warp's slot (tile boundary: filled by cp.async one macro-step ago) ----
@@ -139,15 +159,20 @@ __device__ __forceinline__ void zline_run(const ZCtx &cx_) {
       if (c_.j_first) {
         if (c_.j_zero) { fj[0] = fj[1] = fj[2] = fj[3] = 0.0; }
         else {
-          const double2 a = c_.fjx[(par ^ 1) * (2 * JS) + threadIdx.x], b = c_.fjx[(par ^ 1) * (2 * JS) + JS + threadIdx.x];
+          const double2 a = c_.fjx[rcur * (2 * JS) + threadIdx.x], b = c_.fjx[rcur * (2 * JS) + JS + threadIdx.x];
           fj[0] = a.x; fj[1] = a.y; fj[2] = b.x; fj[3] = b.y;
         }
       } else {
 #pragma unroll
         for (int u = 0; u < 4; ++u) fj[u] = sj[u];
       }
-      if (c_.k_first && c_.k_zero) { fk[0] = fk[1] = fk[2] = fk[3] = 0.0; }
-      else {
+      if (c_.k_first) {
+        if (c_.k_zero) { fk[0] = fk[1] = fk[2] = fk[3] = 0.0; }
+        else {
+          const double2 a = c_.fkin[rcur * (2 * JS) + threadIdx.x], b = c_.fkin[rcur * (2 * JS) + JS + threadIdx.x];
+          fk[0] = a.x; fk[1] = a.y; fk[2] = b.x; fk[3] = b.y;
+        }
+      } else {
         const double2 a = c_.fkx[(par ^ 1) * (2 * XS) + warp * 32 + lane], b = c_.fkx[(par ^ 1) * (2 * XS) + XS + warp * 32 + lane];
         fk[0] = a.x; fk[1] = a.y; fk[2] = b.x; fk[3] = b.y;
       }
@@ -184,7 +209,7 @@ __device__ __forceinline__ void zline_run(const ZCtx &cx_) {
         fi = p2 - fi;
         p4[m] = p; oj[m] = p2 - fj[m]; ok[m] = p2 - fk[m];
       }
-      stg256(c_.psi_b + (eoff + c_.row_off + i0), p4);
+      if (!(c_.exp & 2)) stg256(c_.psi_b + (eoff + c_.row_off + i0), p4);
       if (c == nb - 1) {
         const unsigned ix = (unsigned)d * c_.ipd + (unsigned)g * c_.ipg + c_.ip_idx;
         c_.ipl[ix] = fi;
@@ -204,20 +229,23 @@ __device__ __forceinline__ void zline_run(const ZCtx &cx_) {
         c_.fkx[par * (2 * XS) + XS + (warp + 1) * 32 + lane] = make_double2(ok[2], ok[3]);
       }
     }
-    cp_async_wait_all();
-    __syncthreads();
+    if (!(c_.exp & 8)) cp_async_wait_but_one();  // the boundary faces of the NEXT macro-step have landed; the newest group may still fly
+    if (!(c_.exp & 8)) __syncthreads();
+    ring = rcur;
   }
+  cp_async_wait_all();
 }
 
 template <bool EXACT>
 __global__ void __launch_bounds__(ZW * 32, 1) sweep_zline_kernel(const kb200_sweep_desc *__restrict__ descs, ZGeom gm) {
   extern __shared__ __align__(16) unsigned char zsm[];
-  // shared memory: k-face exchange [2 buffers][2 halves][(ZW+1)*32] double2, j-boundary staging
-  // [2][2][ZW*32] double2, then the per-direction coefficient tables
+  // shared memory: k-face exchange [2 buffers][2 halves][(ZW+1)*32] double2, tile-boundary staging rings for the
+  // j and k faces [3 slots][2 halves][ZW*32] double2 each, then the per-direction coefficient tables
   ZCtx c;
   c.fkx = reinterpret_cast<double2 *>(zsm);
   c.fjx = c.fkx + 2 * 2 * (ZW + 1) * 32;
-  double *cxt = reinterpret_cast<double *>(c.fjx + 2 * 2 * ZW * 32);  // [Ds]   2*xcos/dx[0]
+  c.fkin = c.fjx + 3 * 2 * ZW * 32;
+  double *cxt = reinterpret_cast<double *>(c.fkin + 3 * 2 * ZW * 32);  // [Ds]   2*xcos/dx[0]
   double *txc = cxt + gm.Ds;                                           // [Ds]   2*xcos
   double *cyt = txc + gm.Ds;                                           // [Ds][32]
   double *czt = cyt + (size_t)gm.Ds * 32;                              // [Ds][ZW]
@@ -269,6 +297,8 @@ __global__ void __launch_bounds__(ZW * 32, 1) sweep_zline_kernel(const kb200_swe
   c.rhs_b = ds.rhs; c.sigt_b = ds.sigt; c.psi_b = ds.psi;
   c.ipl = ds.i_plane; c.jpl = ds.j_plane; c.kpl = ds.k_plane;
   c.dx = ds.dx;
+  c.exp = gm.exp;
+  if (gm.exp & 16) { c.j_zero = c.k_zero = c.i_zero = true; c.j_last = c.k_last = false; }
 
   // per-direction coefficient tables (2*cos/delta, SweepSubdomain.cpp:88-93)
   for (int d = threadIdx.x; d < Ds; d += blockDim.x) {
@@ -331,11 +361,12 @@ int kb200_sweep_zline_try(const kb200_sweep_desc *h, int n, const void *d_descs,
   ZGeom gm;
   gm.layout = layout; gm.Ds = h[0].Ds; gm.Gs = h[0].Gs; gm.ni = h[0].ni; gm.nj = h[0].nj; gm.nk = h[0].nk;
   gm.nb = gm.ni / 4;
+  { const char *x = getenv("KB200_ZEXP"); gm.exp = x ? atoi(x) : 0; }
   gm.jw = pow2_ceil(gm.nj, 32);
   gm.kw = pow2_ceil(gm.nk, ZW);
   gm.ntj = (gm.nj + gm.jw - 1) / gm.jw;
   gm.ntk = (gm.nk + gm.kw - 1) / gm.kw;
-  const size_t smem = (size_t)2 * 2 * ((ZW + 1) * 32 + ZW * 32) * sizeof(double2) + (size_t)gm.Ds * (2 + 32 + ZW) * sizeof(double);
+  const size_t smem = ((size_t)2 * 2 * (ZW + 1) * 32 + (size_t)2 * 3 * 2 * ZW * 32) * sizeof(double2) + (size_t)gm.Ds * (2 + 32 + ZW) * sizeof(double);
   // the kernel indexes every chunk with 32-bit element offsets
   if ((double)gm.Ds * gm.Gs * gm.ni * gm.nj * gm.nk >= 2147483648.0) return -1;
   if (smem > 200 * 1024) return -1;
