@@ -1,0 +1,250 @@
+// Scattering on the fp64 tensor-core pipe (mma.sync m8n8k4 f64) for the zone-fastest storage orders
+// (DGZ, GDZ).  Reference: src/Kripke/Kernel/Scattering.cpp:73-99.
+//
+//   phi_out(nm,g,z) (+)= sum_{src set s} sum_{gp} sigs_z(n(nm), g, gp, z) * phi_s(nm,gp,z)
+//   sigs_z = sum_{mix in zone z} sigs(mat(mix), n, g, gp) * fraction(mix)
+//
+// For a fixed moment nm this is a [Gs x G] * [G x Zs] product whose matrix depends on the zone only
+// through the material mix.  Writing f_m(z) for the volume fraction of material m in zone z (0 if
+// absent) gives   phi_out(:,z) = sum_m S_{m,n} * (f_m(z) * phi(:,z)),   i.e. one tensor-core
+// product per material PRESENT in the 8-zone column block of a warp, with the B fragment scaled by
+// the per-zone fraction.  Pure single-material blocks -- all but the material interfaces of the
+// Kobayashi geometry -- take exactly one product with f = 1.0.  At BASELINE config 2/3 the kernel
+// is fp64-bound (G/8 = 8..16 flop/byte), so the contraction runs on the DMMA pipe; the moments are
+// the batch dimension and the three S_{m,n} matrices of the current Legendre order live in shared
+// memory in fragment-major form (rebuilt when n(nm) changes, which happens L times per CTA).
+// The streamed operand uses the same 3-stage cp.async slab pipeline as kb200_moments_mma.cu.
+// EXACT mode (bit-ordered like the reference) uses the DFMA kernel in kb200_scatter_pop.cu.
+#include "kb200_common.cuh"
+
+namespace kb200 {
+
+struct ScatGeom {
+  int layout, M, L1, G, Gs, Zs, nsrc, accumulate;
+  int O, K, nkc4;          // outputs of one o-chunk launch slice (<= 32 per CTA), reduction length, k-chunks
+  int KC, nst;             // slab rows, slabs per tile
+  long long in_b, in_r;    // moment (batch) stride, group (row) stride of phi / phi_out
+  int ntn;                 // zone tiles
+};
+
+__device__ __forceinline__ void sc_cp_async16_zfill(void *smem_dst, const void *gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void sc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void sc_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void sc_dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int SC_STAGES = 3;
+constexpr int SC_QP = 4, SC_NB = 2, SC_NT = 64 * SC_NB, SC_NTP = SC_NT + 4;
+
+__global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scattering_desc *__restrict__ descs, ScatGeom gm) {
+  extern __shared__ __align__(16) double ssm[];
+  constexpr int QP = SC_QP, NB = SC_NB, NT = SC_NT, NTP = SC_NTP;
+  constexpr int PPR = NT / 2, RPP = 256 / PPR;
+  const kb200_scattering_desc &ds = descs[blockIdx.y];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Gs = gm.Gs, K = gm.K, KC = gm.KC, nst = gm.nst, ntn = gm.ntn;
+  const int o_base = blockIdx.z * 8 * QP;                  // first destination group of this o-chunk
+  const int O = min(8 * QP, gm.O - o_base);                // valid destination groups in the chunk
+  double *Ws = ssm;                                        // [3 materials][nkc4][QP][32] fragment-major
+  double *slab = ssm + (size_t)3 * gm.nkc4 * QP * 32;      // [SC_STAGES][KC][NTP]
+  const Strides4 ss = strides_sigs(gm.layout, gm.L1, gm.G);
+
+  const long long ntiles = (long long)gm.M * ntn;          // tile = (moment, zone tile), moment-major
+  const int my_tiles = ((long long)blockIdx.x < ntiles) ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  const int nitems = my_tiles * nst;
+
+  // producer cursor
+  int i_left = nitems, i_st = 0, i_tn = (int)(blockIdx.x % ntn), i_b = (int)(blockIdx.x / ntn), i_buf = 0;
+  int i_s0 = 0, i_g0 = 0;  // (source set, group) of the slab's first row
+  const int c2 = threadIdx.x % PPR, r0 = threadIdx.x / PPR;
+  auto issue = [&]() {
+    if (i_left > 0) {
+      double *dst = slab + (size_t)i_buf * KC * NTP + 2 * c2;
+      const int n = i_tn * NT + 2 * c2;
+      const bool ncol = n < gm.Zs;
+      const long long boff = (long long)i_b * gm.in_b + n;
+      for (int r = r0; r < KC; r += RPP) {
+        int gq = i_g0 + r, sset = i_s0;
+        while (gq >= Gs) { gq -= Gs; ++sset; }
+        const bool valid = ncol && sset < gm.nsrc;
+        const double *src = valid ? ds.phi_src[sset] + (boff + (long long)gq * gm.in_r) : ds.phi_src[0];
+        sc_cp_async16_zfill(dst + (size_t)r * NTP, src, valid);
+      }
+      --i_left;
+      if (++i_st == nst) {
+        i_st = 0; i_s0 = 0; i_g0 = 0;
+        i_tn += gridDim.x;
+        while (i_tn >= ntn) { i_tn -= ntn; ++i_b; }
+      } else {
+        i_g0 += KC;
+        while (i_g0 >= Gs) { i_g0 -= Gs; ++i_s0; }
+      }
+    }
+    sc_cp_async_commit();
+    if (++i_buf == SC_STAGES) i_buf = 0;
+  };
+#pragma unroll
+  for (int s = 0; s < SC_STAGES - 1; ++s) issue();
+
+  double acc[QP][NB][2];
+  double frac[3][NB];
+  unsigned present = 0;  // bit (3*nb + m): material m occurs in column block nb of this warp
+  const int ncol0 = warp * 8 * NB;
+  int st = 0, tn = (int)(blockIdx.x % ntn), b = (int)(blockIdx.x / ntn), cbuf = 0;
+  int n_cur = -1;
+
+  for (int item = 0; item < nitems; ++item) {
+    sc_cp_async_wait<SC_STAGES - 2>();
+    __syncthreads();
+    issue();
+
+    if (st == 0) {
+      // (re)build the three material matrices of this Legendre order, fragment-major, zero padded
+      const int n_leg = ds.moment_to_legendre[b];
+      if (n_leg != n_cur) {
+        n_cur = n_leg;
+        for (int idx = threadIdx.x; idx < 3 * gm.nkc4 * QP * 32; idx += 256) {
+          const int l = idx & 31, f = idx >> 5, ot = f % QP, kc = (f / QP) % gm.nkc4, mat = f / (QP * gm.nkc4);
+          const int o = 8 * ot + (l >> 2), k = 4 * kc + (l & 3);
+          double v = 0.0;
+          if (o < O && k < K) {
+            const int sset = k / Gs, gp = k - sset * Gs;
+            v = ds.sigs[(long long)mat * ss.mat + (long long)n_leg * ss.n + (long long)(ds.glower_dst + o_base + o) * ss.g +
+                        (long long)(ds.glower_src[sset] + gp) * ss.gp];
+          }
+          Ws[idx] = v;
+        }
+        __syncthreads();
+      }
+      // material fractions of this lane's B-fragment columns
+      present = 0;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const int z = tn * NT + ncol0 + 8 * nb + (lane >> 2);
+        frac[0][nb] = frac[1][nb] = frac[2][nb] = 0.0;
+        if (z < gm.Zs) {
+          const int m0 = ds.zone_to_mixelem[z], nmix = ds.zone_to_num_mixelem[z];
+          for (int k = 0; k < nmix; ++k) {
+            const int mat = ds.mixelem_to_material[m0 + k];
+            const double fr = ds.mixelem_to_fraction[m0 + k];
+            if (mat == 0) frac[0][nb] += fr; else if (mat == 1) frac[1][nb] += fr; else frac[2][nb] += fr;
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+          if (__any_sync(0xffffffffu, frac[m][nb] != 0.0)) present |= 1u << (3 * nb + m);
+      }
+#pragma unroll
+      for (int a = 0; a < QP; ++a)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) acc[a][nb][0] = acc[a][nb][1] = 0.0;
+    }
+
+    const double *buf = slab + (size_t)cbuf * KC * NTP;
+    const int kc_lo = st * (KC / 4);
+    const int nkc = min(gm.nkc4 - kc_lo, KC / 4);
+    const double *brow = buf + (size_t)(lane & 3) * NTP + ncol0 + (lane >> 2);
+    for (int kc = 0; kc < nkc; ++kc, brow += 4 * NTP) {
+      double bf[NB];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) bf[nb] = brow[8 * nb];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const unsigned mm = (present >> m) & 0x9u;  // bit0: nb 0, bit3: nb 1
+        if (mm) {
+          const double *wf = Ws + (((size_t)m * gm.nkc4 + kc_lo + kc) * QP) * 32 + lane;
+          double af[QP];
+#pragma unroll
+          for (int a = 0; a < QP; ++a) af[a] = wf[a * 32];
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            if (mm & (1u << (3 * nb))) {
+              const double bm = bf[nb] * frac[m][nb];
+#pragma unroll
+              for (int a = 0; a < QP; ++a) sc_dmma884(acc[a][nb][0], acc[a][nb][1], af[a], bm);
+            }
+          }
+        }
+      }
+    }
+
+    if (st == nst - 1) {
+      const int ncol = tn * NT + ncol0 + 2 * (lane & 3);
+#pragma unroll
+      for (int a = 0; a < QP; ++a) {
+        const int o = 8 * a + (lane >> 2);
+        if (o < O) {
+          double *row = ds.phi_out + ((long long)b * gm.in_b + (long long)(o_base + o) * gm.in_r);
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            const int n = ncol + 8 * nb;
+            if (n < gm.Zs) {
+              double2 v = make_double2(acc[a][nb][0], acc[a][nb][1]);
+              double2 *p = reinterpret_cast<double2 *>(row + n);
+              if (gm.accumulate) { const double2 old = *p; v.x += old.x; v.y += old.y; }
+              *p = v;
+            }
+          }
+        }
+      }
+    }
+    if (++cbuf == SC_STAGES) cbuf = 0;
+    if (++st == nst) {
+      st = 0;
+      tn += gridDim.x;
+      while (tn >= ntn) { tn -= ntn; ++b; }
+    }
+  }
+  sc_cp_async_wait<0>();
+}
+
+}  // namespace kb200
+
+using namespace kb200;
+
+// Returns 0 if handled, -1 if this path does not apply (caller falls back to the DFMA kernel), >0 on error.
+int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_descs, cudaStream_t st) {
+  const int layout = h[0].layout;
+  if (layout != 0 && layout != 2) return -1;
+  const char *env = getenv("KB200_SCATTER_DFMA");
+  if (env && env[0] == '1') return -1;
+  if (h[0].Zs % 2 != 0) return -1;
+  for (int i = 0; i < n; ++i) {
+    if (h[i].nsrc != h[0].nsrc || h[i].accumulate != h[0].accumulate || h[i].G != h[0].G || h[i].L1 != h[0].L1) return -1;
+    if (((uintptr_t)h[i].phi_out & 15) != 0) return -1;
+    for (int s = 0; s < h[i].nsrc; ++s)
+      if (((uintptr_t)h[i].phi_src[s] & 15) != 0) return -1;
+  }
+  ScatGeom gm;
+  memset(&gm, 0, sizeof(gm));
+  gm.layout = layout; gm.M = h[0].M; gm.L1 = h[0].L1; gm.G = h[0].G; gm.Gs = h[0].Gs; gm.Zs = h[0].Zs;
+  gm.nsrc = h[0].nsrc; gm.accumulate = h[0].accumulate;
+  gm.O = gm.Gs; gm.K = gm.nsrc * gm.Gs; gm.nkc4 = (gm.K + 3) / 4;
+  const int Kp = gm.nkc4 * 4;
+  gm.KC = Kp < 16 ? Kp : 16;
+  gm.nst = (Kp + gm.KC - 1) / gm.KC;
+  const Strides3 ms = strides_dgz(layout, gm.M, gm.Gs, gm.Zs);
+  gm.in_b = ms.a; gm.in_r = ms.g;
+  gm.ntn = (gm.Zs + SC_NT - 1) / SC_NT;
+  const size_t smem = ((size_t)3 * gm.nkc4 * SC_QP * 32 + (size_t)SC_STAGES * gm.KC * SC_NTP) * sizeof(double);
+  if (smem > 200 * 1024) return -1;
+  KB_CUDA(cudaFuncSetAttribute(scatter_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nochunks = (gm.O + 8 * SC_QP - 1) / (8 * SC_QP);
+  const long long ntiles = (long long)gm.M * gm.ntn;
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2) per_sm = 2;
+  long long ctas = (long long)sm_count() * per_sm / ((long long)n * nochunks);
+  if (ctas < 1) ctas = 1;
+  if (ctas > ntiles) ctas = ntiles;
+  dim3 grid((unsigned)ctas, n, nochunks);
+  scatter_mma_kernel<<<grid, 256, smem, st>>>((const kb200_scattering_desc *)d_descs, gm);
+  return post_launch("scatter_mma");
+}
