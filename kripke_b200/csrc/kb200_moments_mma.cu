@@ -68,6 +68,9 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
   constexpr int RPP = 256 / PPR;             // slab rows filled per pass of the CTA
   double *Ws = msm;                                         // [nkc4][q][32] fragment-major weights
   double *slab = msm + (size_t)gm.nkc4 * gm.q * 32;         // [MMA_STAGES][KC][NTP]
+  // row base pointers (batch 0, column 0) of the streamed rows / produced rows, null when padded
+  const double **inrow = reinterpret_cast<const double **>(slab + (size_t)MMA_STAGES * gm.KC * NTP);  // [nst*KC]
+  double **outrow = reinterpret_cast<double **>(slab + (size_t)MMA_STAGES * gm.KC * NTP + (size_t)gm.nst * gm.KC);  // [8*q]
   const MomentsDescK dsc = descs[blockIdx.y];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int M = gm.M, Ds = gm.Ds, O = gm.O, K = gm.K, q = gm.q, KC = gm.KC;
@@ -83,6 +86,23 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
     }
     Ws[idx] = v;
   }
+  for (int k = threadIdx.x; k < gm.nst * KC; k += 256) {
+    const double *p = nullptr;
+    if (k < K) {
+      if (gm.mode == 0) { const int s = k / Ds, d = k - s * Ds; p = dsc.in[s] + (long long)d * gm.in_r; }
+      else p = dsc.in[0] + (long long)k * gm.in_r;
+    }
+    inrow[k] = p;
+  }
+  for (int o = threadIdx.x; o < 8 * q; o += 256) {
+    double *p = nullptr;
+    if (o < O) {
+      if (gm.mode == 0) p = dsc.out[0] + (long long)o * gm.out_r;
+      else { const int s = o / Ds, d = o - s * Ds; p = dsc.out[s] + (long long)d * gm.out_r; }
+    }
+    outrow[o] = p;
+  }
+  __syncthreads();
 
   // all loop control is 32-bit and incremental (no divisions inside the pipeline)
   const int ntn = (int)gm.ntn, nst = gm.nst;
@@ -92,37 +112,25 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
 
   // producer cursor: next slab to fetch
   int i_left = nitems, i_st = 0, i_tn = (int)(blockIdx.x % gm.ntn), i_b = (int)(blockIdx.x / gm.ntn), i_buf = 0;
-  int i_s0 = 0, i_d0 = 0;  // (direction set, direction) of the slab's first row (LTimes)
   const int c2 = threadIdx.x % PPR, r0 = threadIdx.x / PPR;
   auto issue = [&]() {
     if (i_left > 0) {
-      double *dst = slab + (size_t)i_buf * KC * NTP + 2 * c2;
+      double *dst = slab + (size_t)i_buf * KC * NTP + 2 * c2 + (size_t)r0 * NTP;
       const long long n = (long long)i_tn * NT + 2 * c2;
       const bool ncol = n < gm.N;
       const long long boff = (long long)i_b * gm.in_b + n;
-      for (int r = r0; r < KC; r += RPP) {
-        bool valid = ncol;
-        const double *src = dsc.in[0];
-        if (gm.mode == 0) {
-          int d = i_d0 + r, sset = i_s0;
-          while (d >= Ds) { d -= Ds; ++sset; }
-          valid = valid && sset < gm.nsets;
-          if (valid) src = dsc.in[sset] + (boff + (long long)d * gm.in_r);
-        } else {
-          const int k = i_st * KC + r;
-          valid = valid && k < K;
-          if (valid) src += boff + (long long)k * gm.in_r;
-        }
-        cp_async16_zfill(dst + (size_t)r * NTP, src, valid);
+      const double *const *rp = inrow + i_st * KC + r0;
+#pragma unroll 4
+      for (int r = r0; r < KC; r += RPP, rp += RPP, dst += (size_t)RPP * NTP) {
+        const double *base = *rp;
+        const bool valid = ncol && base != nullptr;
+        cp_async16_zfill(dst, valid ? base + boff : dsc.in[0], valid);
       }
       --i_left;
       if (++i_st == nst) {
-        i_st = 0; i_s0 = 0; i_d0 = 0;
+        i_st = 0;
         i_tn += gridDim.x;
         while (i_tn >= ntn) { i_tn -= ntn; ++i_b; }
-      } else {
-        i_d0 += KC;
-        while (i_d0 >= Ds) { i_d0 -= Ds; ++i_s0; }
       }
     }
     cp_async_commit();
@@ -191,9 +199,7 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
         for (int a = 0; a < QP; ++a) {
           const int o = 8 * (ot0 + a) + (lane >> 2);
           if (ot0 + a < q && o < O) {
-            double *row;
-            if (gm.mode == 0) row = dsc.out[0] + ((long long)b * gm.out_b + (long long)o * gm.out_r);
-            else { const int sset = o / Ds, d = o - sset * Ds; row = dsc.out[sset] + ((long long)b * gm.out_b + (long long)d * gm.out_r); }
+            double *row = outrow[o] + (long long)b * gm.out_b;
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) {
               const long long n = ncol + 8 * nb;
@@ -225,7 +231,7 @@ using namespace kb200;
 template <int QP, int NB>
 static int launch_mma(const MomentsDescK *d_views, int n, const MmaGeom &gm, cudaStream_t st) {
   constexpr int NT = 64 * NB, NTP = NT + 4;
-  const size_t smem = ((size_t)gm.nkc4 * gm.q * 32 + (size_t)MMA_STAGES * gm.KC * NTP) * sizeof(double);
+  const size_t smem = ((size_t)gm.nkc4 * gm.q * 32 + (size_t)MMA_STAGES * gm.KC * NTP + (size_t)gm.nst * gm.KC + 8 * gm.q) * sizeof(double);
   if (smem > 200 * 1024) return -1;
   auto k = moments_mma_kernel<QP, NB>;
   KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

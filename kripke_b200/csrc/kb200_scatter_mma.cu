@@ -54,6 +54,13 @@ __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scatter
   const int O = min(8 * QP, gm.O - o_base);                // valid destination groups in the chunk
   double *Ws = ssm;                                        // [3 materials][nkc4][QP][32] fragment-major
   double *slab = ssm + (size_t)3 * gm.nkc4 * QP * 32;      // [SC_STAGES][KC][NTP]
+  const double **inrow = reinterpret_cast<const double **>(slab + (size_t)SC_STAGES * gm.KC * NTP);  // [nst*KC] row bases
+  for (int k = threadIdx.x; k < gm.nst * gm.KC; k += 256) {
+    const double *p = nullptr;
+    if (k < gm.K) { const int sset = k / gm.Gs, gq = k - sset * gm.Gs; p = ds.phi_src[sset] + (long long)gq * gm.in_r; }
+    inrow[k] = p;
+  }
+  __syncthreads();
   const Strides4 ss = strides_sigs(gm.layout, gm.L1, gm.G);
 
   const long long ntiles = (long long)gm.M * ntn;          // tile = (moment, zone tile), moment-major
@@ -62,29 +69,25 @@ __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scatter
 
   // producer cursor
   int i_left = nitems, i_st = 0, i_tn = (int)(blockIdx.x % ntn), i_b = (int)(blockIdx.x / ntn), i_buf = 0;
-  int i_s0 = 0, i_g0 = 0;  // (source set, group) of the slab's first row
   const int c2 = threadIdx.x % PPR, r0 = threadIdx.x / PPR;
   auto issue = [&]() {
     if (i_left > 0) {
-      double *dst = slab + (size_t)i_buf * KC * NTP + 2 * c2;
+      double *dst = slab + (size_t)i_buf * KC * NTP + 2 * c2 + (size_t)r0 * NTP;
       const int n = i_tn * NT + 2 * c2;
       const bool ncol = n < gm.Zs;
       const long long boff = (long long)i_b * gm.in_b + n;
-      for (int r = r0; r < KC; r += RPP) {
-        int gq = i_g0 + r, sset = i_s0;
-        while (gq >= Gs) { gq -= Gs; ++sset; }
-        const bool valid = ncol && sset < gm.nsrc;
-        const double *src = valid ? ds.phi_src[sset] + (boff + (long long)gq * gm.in_r) : ds.phi_src[0];
-        sc_cp_async16_zfill(dst + (size_t)r * NTP, src, valid);
+      const double *const *rp = inrow + i_st * KC + r0;
+#pragma unroll 4
+      for (int r = r0; r < KC; r += RPP, rp += RPP, dst += (size_t)RPP * NTP) {
+        const double *base = *rp;
+        const bool valid = ncol && base != nullptr;
+        sc_cp_async16_zfill(dst, valid ? base + boff : ds.phi_out, valid);
       }
       --i_left;
       if (++i_st == nst) {
-        i_st = 0; i_s0 = 0; i_g0 = 0;
+        i_st = 0;
         i_tn += gridDim.x;
         while (i_tn >= ntn) { i_tn -= ntn; ++i_b; }
-      } else {
-        i_g0 += KC;
-        while (i_g0 >= Gs) { i_g0 -= Gs; ++i_s0; }
       }
     }
     sc_cp_async_commit();
@@ -233,7 +236,7 @@ int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_d
   const Strides3 ms = strides_dgz(layout, gm.M, gm.Gs, gm.Zs);
   gm.in_b = ms.a; gm.in_r = ms.g;
   gm.ntn = (gm.Zs + SC_NT - 1) / SC_NT;
-  const size_t smem = ((size_t)3 * gm.nkc4 * SC_QP * 32 + (size_t)SC_STAGES * gm.KC * SC_NTP) * sizeof(double);
+  const size_t smem = ((size_t)3 * gm.nkc4 * SC_QP * 32 + (size_t)SC_STAGES * gm.KC * SC_NTP + (size_t)gm.nst * gm.KC) * sizeof(double);
   if (smem > 200 * 1024) return -1;
   KB_CUDA(cudaFuncSetAttribute(scatter_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nochunks = (gm.O + 8 * SC_QP - 1) / (8 * SC_QP);
