@@ -60,7 +60,9 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 
 constexpr int MMA_STAGES = 3;
 
-template <int QP, int NB>
+// XMODE 1: O = 8*q + 1, the last output row is accumulated with DFMA on the B-fragment layout (LTimes, M = 25)
+// XMODE 2: K = 4*nkc4 + 1, the last reduction row is added with DFMA on the C-fragment layout (LPlusTimes, M = 25)
+template <int QP, int NB, int XMODE>
 __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(const MomentsDescK *__restrict__ descs, MmaGeom gm) {
   extern __shared__ __align__(16) double msm[];
   constexpr int NT = 64 * NB, NTP = NT + 4;  // row stride = 4 (mod 16) doubles: conflict-free B fragments
@@ -70,7 +72,8 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
   double *slab = msm + (size_t)gm.nkc4 * gm.q * 32;         // [MMA_STAGES][KC][NTP]
   // row base pointers (batch 0, column 0) of the streamed rows / produced rows, null when padded
   const double **inrow = reinterpret_cast<const double **>(slab + (size_t)MMA_STAGES * gm.KC * NTP);  // [nst*KC]
-  double **outrow = reinterpret_cast<double **>(slab + (size_t)MMA_STAGES * gm.KC * NTP + (size_t)gm.nst * gm.KC);  // [8*q]
+  double **outrow = reinterpret_cast<double **>(slab + (size_t)MMA_STAGES * gm.KC * NTP + (size_t)gm.nst * gm.KC);  // [8*q+8]
+  double *wx = reinterpret_cast<double *>(outrow + 8 * gm.q + 8);  // XMODE 1: [nst*KC] W[O-1][k] ; XMODE 2: [8*q] W[o][K-1]
   const MomentsDescK dsc = descs[blockIdx.y];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int M = gm.M, Ds = gm.Ds, O = gm.O, K = gm.K, q = gm.q, KC = gm.KC;
@@ -94,7 +97,19 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
     }
     inrow[k] = p;
   }
-  for (int o = threadIdx.x; o < 8 * q; o += 256) {
+  if (XMODE == 1)
+    for (int k = threadIdx.x; k < gm.nst * KC; k += 256) {
+      double v = 0.0;
+      if (k < K) { const int s = k / Ds, d = k - s * Ds; v = dsc.w[s][(size_t)d * M + (O - 1)]; }
+      wx[k] = v;
+    }
+  if (XMODE == 2)
+    for (int o = threadIdx.x; o < 8 * q; o += 256) {
+      double v = 0.0;
+      if (o < O) { const int s = o / Ds, d = o - s * Ds; v = dsc.w[s][(size_t)d * M + (K - 1)]; }
+      wx[o] = v;
+    }
+  for (int o = threadIdx.x; o < 8 * q + 8; o += 256) {
     double *p = nullptr;
     if (o < O) {
       if (gm.mode == 0) p = dsc.out[0] + (long long)o * gm.out_r;
@@ -112,16 +127,19 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
 
   // producer cursor: next slab to fetch
   int i_left = nitems, i_st = 0, i_tn = (int)(blockIdx.x % gm.ntn), i_b = (int)(blockIdx.x / gm.ntn), i_buf = 0;
-  const int c2 = threadIdx.x % PPR, r0 = threadIdx.x / PPR;
+  // every warp copies and consumes only its own 8*NB columns of a slab: no CTA-wide barrier in the pipeline
+  constexpr int PW = 4 * NB, RPW = 32 / PW;  // 16-byte pieces per row per warp, rows per warp instruction
+  const int c2 = lane % PW, r0 = lane / PW;
+  const int wcol0 = warp * 8 * NB;
   auto issue = [&]() {
     if (i_left > 0) {
-      double *dst = slab + (size_t)i_buf * KC * NTP + 2 * c2 + (size_t)r0 * NTP;
-      const long long n = (long long)i_tn * NT + 2 * c2;
+      double *dst = slab + (size_t)i_buf * KC * NTP + wcol0 + 2 * c2 + (size_t)r0 * NTP;
+      const long long n = (long long)i_tn * NT + wcol0 + 2 * c2;
       const bool ncol = n < gm.N;
       const long long boff = (long long)i_b * gm.in_b + n;
       const double *const *rp = inrow + i_st * KC + r0;
 #pragma unroll 4
-      for (int r = r0; r < KC; r += RPP, rp += RPP, dst += (size_t)RPP * NTP) {
+      for (int r = r0; r < KC; r += RPW, rp += RPW, dst += (size_t)RPW * NTP) {
         const double *base = *rp;
         const bool valid = ncol && base != nullptr;
         cp_async16_zfill(dst, valid ? base + boff : dsc.in[0], valid);
@@ -141,13 +159,14 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
   for (int s = 0; s < MMA_STAGES - 1; ++s) issue();
 
   double acc[QP][NB][2];
+  double px[NB];  // XMODE 1: partial sums of the extra output row (this lane's k residue class)
   const int ncol0 = warp * 8 * NB;  // this warp's first column inside the tile
   // consumer cursor
   int st = 0, tn = (int)(blockIdx.x % gm.ntn), b = (int)(blockIdx.x / gm.ntn), cbuf = 0;
 
   for (int item = 0; item < nitems; ++item) {
     cp_async_wait<MMA_STAGES - 2>();
-    __syncthreads();  // slab `item` has landed for everyone; slab item-1 is free (also orders the Ws build)
+    __syncwarp();  // this warp's columns of slab `item` have landed; its columns of slab item-1 are free
     issue();
 
     const double *buf = slab + (size_t)cbuf * KC * NTP;
@@ -161,6 +180,8 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
         for (int a = 0; a < QP; ++a)
 #pragma unroll
           for (int nb = 0; nb < NB; ++nb) acc[a][nb][0] = acc[a][nb][1] = 0.0;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) px[nb] = 0.0;
       }
       const int ot0 = pass * QP;
       const double *wf = Ws + ((size_t)kc_lo * q + ot0) * 32 + lane;
@@ -177,6 +198,11 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
           for (int a = 0; a < QP; ++a)
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) dmma884(acc[a][nb][0], acc[a][nb][1], af[a], bf[nb]);
+          if (XMODE == 1) {
+            const double wxk = wx[4 * (kc_lo + kc) + (lane & 3)];
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) px[nb] = fma(wxk, bf[nb], px[nb]);
+          }
         }
       } else {
         for (int kc = 0; kc < nkc; ++kc, brow += 4 * NTP, wf += q * 32) {
@@ -190,6 +216,40 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
 #pragma unroll
               for (int nb = 0; nb < NB; ++nb) dmma884(acc[a][nb][0], acc[a][nb][1], af, bf[nb]);
             }
+          }
+          if (XMODE == 1) {
+            const double wxk = wx[4 * (kc_lo + kc) + (lane & 3)];
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) px[nb] = fma(wxk, bf[nb], px[nb]);
+          }
+        }
+      }
+      if (XMODE == 2) {  // the reduction row K-1 on the C-fragment layout
+        const double *xr = buf + (size_t)(K - 1) * NTP + ncol0 + 2 * (lane & 3);
+#pragma unroll
+        for (int a = 0; a < QP; ++a) {
+          if (ot0 + a < q) {
+            const double wk = wx[8 * (ot0 + a) + (lane >> 2)];
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+              const double2 xin = *reinterpret_cast<const double2 *>(xr + 8 * nb);
+              acc[a][nb][0] = fma(wk, xin.x, acc[a][nb][0]);
+              acc[a][nb][1] = fma(wk, xin.y, acc[a][nb][1]);
+            }
+          }
+        }
+      }
+      if (XMODE == 1 && st == nst - 1) {  // extra output row: sum the four k residue classes, one lane per column stores
+        double *row = outrow[O - 1] + (long long)b * gm.out_b;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          double v = px[nb];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          const long long n = (long long)tn * NT + ncol0 + 8 * nb + (lane >> 2);
+          if ((lane & 3) == 0 && n < gm.N) {
+            if (gm.accumulate) v += row[n];
+            row[n] = v;
           }
         }
       }
@@ -228,12 +288,13 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
 
 using namespace kb200;
 
-template <int QP, int NB>
+template <int QP, int NB, int XMODE>
 static int launch_mma(const MomentsDescK *d_views, int n, const MmaGeom &gm, cudaStream_t st) {
   constexpr int NT = 64 * NB, NTP = NT + 4;
-  const size_t smem = ((size_t)gm.nkc4 * gm.q * 32 + (size_t)MMA_STAGES * gm.KC * NTP + (size_t)gm.nst * gm.KC + 8 * gm.q) * sizeof(double);
+  const size_t smem = ((size_t)gm.nkc4 * gm.q * 32 + (size_t)MMA_STAGES * gm.KC * NTP + (size_t)gm.nst * gm.KC + 8 * gm.q + 8 +
+                       (XMODE == 1 ? (size_t)gm.nst * gm.KC : XMODE == 2 ? (size_t)8 * gm.q : 0)) * sizeof(double);
   if (smem > 200 * 1024) return -1;
-  auto k = moments_mma_kernel<QP, NB>;
+  auto k = moments_mma_kernel<QP, NB, XMODE>;
   KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long ntiles = gm.B * gm.ntn;
   int per_sm = (int)((220 * 1024) / (smem + 1024));
@@ -268,24 +329,33 @@ int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, i
   gm.q = (gm.O + 7) / 8;
   gm.nkc4 = (gm.K + 3) / 4;
   const int Kp = gm.nkc4 * 4;
+  const MomentsDescK *dv = (const MomentsDescK *)d_views;
   // regime: all outputs in registers with K streamed, or K resident with output passes
   if (gm.q <= 4 || (gm.q <= 13 && Kp > 32)) {
     gm.KC = Kp < 16 ? Kp : 16;
     gm.nst = (Kp + gm.KC - 1) / gm.KC;
     gm.npass = 1;
     gm.ntn = (gm.N + 127) / 128;
-    if (gm.q <= 4) return launch_mma<4, 2>((const MomentsDescK *)d_views, n, gm, st);
-    return launch_mma<13, 2>((const MomentsDescK *)d_views, n, gm, st);
+    if (gm.q == 4 && gm.O == 25) {  // 3 tensor-core tiles + one DFMA row instead of 4 tiles (22% less fp64 work)
+      gm.q = 3;
+      return launch_mma<3, 2, 1>(dv, n, gm, st);
+    }
+    if (gm.q <= 4) return launch_mma<4, 2, 0>(dv, n, gm, st);
+    return launch_mma<13, 2, 0>(dv, n, gm, st);
   }
   if (Kp <= 32) {  // K resident
     gm.KC = Kp; gm.nst = 1; gm.npass = (gm.q + 3) / 4;
     gm.ntn = (gm.N + 127) / 128;
-    return launch_mma<4, 2>((const MomentsDescK *)d_views, n, gm, st);
+    if (gm.K % 4 == 1 && gm.K > 4) {  // last reduction row by DFMA instead of a 3/4-empty k-chunk
+      gm.nkc4 = gm.K / 4;
+      return launch_mma<4, 2, 2>(dv, n, gm, st);
+    }
+    return launch_mma<4, 2, 0>(dv, n, gm, st);
   }
   if (gm.q <= 16) {  // both large (e.g. Legendre order 9): narrower tiles, all outputs in registers
     gm.KC = 16; gm.nst = (Kp + 15) / 16; gm.npass = 1;
     gm.ntn = (gm.N + 63) / 64;
-    return launch_mma<16, 1>((const MomentsDescK *)d_views, n, gm, st);
+    return launch_mma<16, 1, 0>(dv, n, gm, st);
   }
   return -1;
 }

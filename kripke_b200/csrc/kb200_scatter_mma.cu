@@ -69,16 +69,19 @@ __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scatter
 
   // producer cursor
   int i_left = nitems, i_st = 0, i_tn = (int)(blockIdx.x % ntn), i_b = (int)(blockIdx.x / ntn), i_buf = 0;
-  const int c2 = threadIdx.x % PPR, r0 = threadIdx.x / PPR;
+  // every warp copies and consumes only its own 8*NB columns of a slab: no CTA-wide barrier in the pipeline
+  constexpr int PW = 4 * NB, RPW = 32 / PW;
+  const int c2 = lane % PW, r0 = lane / PW;
+  const int wcol0 = warp * 8 * NB;
   auto issue = [&]() {
     if (i_left > 0) {
-      double *dst = slab + (size_t)i_buf * KC * NTP + 2 * c2 + (size_t)r0 * NTP;
-      const int n = i_tn * NT + 2 * c2;
+      double *dst = slab + (size_t)i_buf * KC * NTP + wcol0 + 2 * c2 + (size_t)r0 * NTP;
+      const int n = i_tn * NT + wcol0 + 2 * c2;
       const bool ncol = n < gm.Zs;
       const long long boff = (long long)i_b * gm.in_b + n;
       const double *const *rp = inrow + i_st * KC + r0;
 #pragma unroll 4
-      for (int r = r0; r < KC; r += RPP, rp += RPP, dst += (size_t)RPP * NTP) {
+      for (int r = r0; r < KC; r += RPW, rp += RPW, dst += (size_t)RPW * NTP) {
         const double *base = *rp;
         const bool valid = ncol && base != nullptr;
         sc_cp_async16_zfill(dst, valid ? base + boff : ds.phi_out, valid);
@@ -105,13 +108,14 @@ __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scatter
 
   for (int item = 0; item < nitems; ++item) {
     sc_cp_async_wait<SC_STAGES - 2>();
-    __syncthreads();
+    __syncwarp();  // per-warp pipeline: only this warp's columns are consumed below
     issue();
 
     if (st == 0) {
       // (re)build the three material matrices of this Legendre order, fragment-major, zero padded
       const int n_leg = ds.moment_to_legendre[b];
-      if (n_leg != n_cur) {
+      if (n_leg != n_cur) {  // CTA-uniform: every warp reaches this item with the same moment index
+        if (n_cur >= 0) __syncthreads();  // nobody still reads the previous matrices
         n_cur = n_leg;
         for (int idx = threadIdx.x; idx < 3 * gm.nkc4 * QP * 32; idx += 256) {
           const int l = idx & 31, f = idx >> 5, ot = f % QP, kc = (f / QP) % gm.nkc4, mat = f / (QP * gm.nkc4);

@@ -72,6 +72,32 @@ def test_lplustimes(gpu, layout, exact):
     gpu.abi().kb200_set_exact(0)
 
 
+MOMENT_SHAPES = [
+    # (legendre, quad): M = 25 exercises the 3-tile + DFMA-row LTimes and the K = 4*6+1 LPlusTimes paths of
+    # kb200_moments_mma.cu; M = 100 the wide-output / streamed-K paths; M = 1 the degenerate one
+    (4, 96), (9, 16), (0, 8), (5, 40),
+]
+
+
+@pytest.mark.parametrize("layout", ["DGZ", "DZG", "GDZ"])
+@pytest.mark.parametrize("shape", range(len(MOMENT_SHAPES)))
+def test_moments_tensor_core_shapes(gpu, shape, layout):
+    L, quad = MOMENT_SHAPES[shape]
+    args = f"--zones 10,6,8 --groups 6 --quad {quad} --legendre {L} --gset 2 --dset 8 --zset 1,2,1 --layout {layout}"
+    p, o, _, _ = pair(gpu, args)
+    fill_both(p, o, "psi", 1100 + shape, -1.0, 2.0)
+    o.zero("phi"); o.ltimes()
+    p.call("zero:phi"); p.call("LTimes")
+    assert_close(p.field("phi"), o.field("phi"), f"LTimes L={L} {layout}", False)
+    fill_both(p, o, "phi_out", 1200 + shape, -1.0, 1.0)
+    o.zero("rhs"); o.lplustimes()
+    p.call("zero:rhs"); p.call("LPlusTimes")
+    assert_close(p.field("rhs"), o.field("rhs"), f"LPlusTimes L={L} {layout}", False)
+    # accumulate semantics (no pending zero-fill): a second call adds on top
+    o.ltimes(); p.call("LTimes")
+    assert_close(p.field("phi"), o.field("phi"), f"LTimes accumulate L={L} {layout}", False)
+
+
 @pytest.mark.parametrize("exact", [False, True])
 @pytest.mark.parametrize("layout", LAYOUTS)
 def test_scattering_and_source_with_dense_asymmetric_sigs(gpu, layout, exact):
