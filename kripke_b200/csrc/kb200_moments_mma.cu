@@ -58,11 +58,10 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-constexpr int MMA_STAGES = 3;
 
 // XMODE 1: O = 8*q + 1, the last output row is accumulated with DFMA on the B-fragment layout (LTimes, M = 25)
 // XMODE 2: K = 4*nkc4 + 1, the last reduction row is added with DFMA on the C-fragment layout (LPlusTimes, M = 25)
-template <int QP, int NB, int XMODE>
+template <int QP, int NB, int XMODE, int MMA_STAGES>
 __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(const MomentsDescK *__restrict__ descs, MmaGeom gm) {
   extern __shared__ __align__(16) double msm[];
   constexpr int NT = 64 * NB, NTP = NT + 4;  // row stride = 4 (mod 16) doubles: conflict-free B fragments
@@ -288,13 +287,13 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
 
 using namespace kb200;
 
-template <int QP, int NB, int XMODE>
+template <int QP, int NB, int XMODE, int MMA_STAGES>
 static int launch_mma(const MomentsDescK *d_views, int n, const MmaGeom &gm, cudaStream_t st) {
   constexpr int NT = 64 * NB, NTP = NT + 4;
   const size_t smem = ((size_t)gm.nkc4 * gm.q * 32 + (size_t)MMA_STAGES * gm.KC * NTP + (size_t)gm.nst * gm.KC + 8 * gm.q + 8 +
                        (XMODE == 1 ? (size_t)gm.nst * gm.KC : XMODE == 2 ? (size_t)8 * gm.q : 0)) * sizeof(double);
   if (smem > 200 * 1024) return -1;
-  auto k = moments_mma_kernel<QP, NB, XMODE>;
+  auto k = moments_mma_kernel<QP, NB, XMODE, MMA_STAGES>;
   KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long ntiles = gm.B * gm.ntn;
   int per_sm = (int)((220 * 1024) / (smem + 1024));
@@ -338,24 +337,24 @@ int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, i
     gm.ntn = (gm.N + 127) / 128;
     if (gm.q == 4 && gm.O == 25) {  // 3 tensor-core tiles + one DFMA row instead of 4 tiles (22% less fp64 work)
       gm.q = 3;
-      return launch_mma<3, 2, 1>(dv, n, gm, st);
+      return launch_mma<3, 2, 1, 3>(dv, n, gm, st);
     }
-    if (gm.q <= 4) return launch_mma<4, 2, 0>(dv, n, gm, st);
-    return launch_mma<13, 2, 0>(dv, n, gm, st);
+    if (gm.q <= 4) return launch_mma<4, 2, 0, 3>(dv, n, gm, st);
+    return launch_mma<13, 2, 0, 3>(dv, n, gm, st);
   }
   if (Kp <= 32) {  // K resident
     gm.KC = Kp; gm.nst = 1; gm.npass = (gm.q + 3) / 4;
     gm.ntn = (gm.N + 127) / 128;
     if (gm.K % 4 == 1 && gm.K > 4) {  // last reduction row by DFMA instead of a 3/4-empty k-chunk
       gm.nkc4 = gm.K / 4;
-      return launch_mma<4, 2, 2>(dv, n, gm, st);
+      return launch_mma<4, 2, 2, 2>(dv, n, gm, st);
     }
-    return launch_mma<4, 2, 0>(dv, n, gm, st);
+    return launch_mma<4, 2, 0, 2>(dv, n, gm, st);
   }
   if (gm.q <= 16) {  // both large (e.g. Legendre order 9): narrower tiles, all outputs in registers
     gm.KC = 16; gm.nst = (Kp + 15) / 16; gm.npass = 1;
     gm.ntn = (gm.N + 63) / 64;
-    return launch_mma<16, 1, 0>(dv, n, gm, st);
+    return launch_mma<16, 1, 0, 3>(dv, n, gm, st);
   }
   return -1;
 }

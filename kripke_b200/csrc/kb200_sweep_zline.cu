@@ -64,7 +64,8 @@ struct ZCtx {
   unsigned sa, sg, Zs;                       // element strides of rhs/psi, zones per subdomain
   unsigned ipd, ipg, jpd, jpg, kpd, kpg;     // element strides of the three planes
   int Ds, ni, nb, jw;
-  int d0, g0, dstep, gstep;                  // first element of the stream and the stream stride
+  int dv, gv, dstep, gstep;                  // virtual predecessor of the stream's first element, stream stride
+  unsigned estep, ewrap, sstep;              // incremental element-offset updates (mod 2^32)
   int T, Hend, jjkk;
   bool line_ok, i_zero, j_zero, k_zero, j_first, k_first, j_last, k_last, uniform_x;
   int exp;
@@ -75,23 +76,28 @@ __device__ __forceinline__ void zline_run(const ZCtx &cx_) {
   const ZCtx c_ = cx_;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nb = c_.nb, ni = c_.ni;
+  // Stream state = the block computed most recently.  Before the first block it is the last block of a
+  // virtual predecessor element, so "the next block" is always derived by the same arithmetic.  All
+  // element offsets are advanced incrementally modulo 2^32 (no multiplications in the loop).
   int c = nb - 1;
-  int d = 0, g = 0, dN = c_.d0, gN = c_.g0;
-  unsigned eoff = 0, soff = 0;
+  int d = c_.dv, g = c_.gv;
+  unsigned eoff = (unsigned)d * c_.sa + (unsigned)g * c_.sg;
+  unsigned soff = (unsigned)g * c_.Zs;
   double cx = 0, cy = 0, cz = 0, csum = 0;
   double r4n[4] = {0, 0, 0, 0}, s4n[4] = {1, 1, 1, 1}, finn = 0.0;
   double fi = 0.0;
   double oj[4] = {0, 0, 0, 0};
   constexpr int XS = (ZW + 1) * 32;  // slots per half-buffer of the k exchange
   constexpr int JS = ZW * 32;        // slots per half-buffer of the boundary staging rings
-  // boundary-face cursor: the block this line will compute two macro-steps from now
-  int cF = 0, dF = c_.d0, gF = c_.g0;
-  int ring = 0;  // (H + 2) mod 3
+  int ring = 0;                      // (H + 2) mod 3
+  const bool bnd_j = c_.j_first && !c_.j_zero, bnd_k = c_.k_first && !c_.k_zero;
 
   int t = -2 - c_.jjkk;
+#pragma unroll 1
   for (int H = -2; H < c_.Hend; ++H, ++t) {  // H < 0 only prefetches the first blocks of line (0,0)
     const bool act = c_.line_ok && (unsigned)t < (unsigned)c_.T;
     const bool pre = c_.line_ok && (unsigned)(t + 1) < (unsigned)c_.T;
+    const bool pre2 = c_.line_ok && (unsigned)(t + 2) < (unsigned)c_.T;
     const int par = H & 1;
 
     double r4[4], s4[4];
@@ -100,57 +106,60 @@ __device__ __forceinline__ void zline_run(const ZCtx &cx_) {
     const double fin = finn;
 
     if (act) {
-      if (++c == nb) {  // next element of the stream
+      if (c == nb - 1) {  // first block of the next element of the stream
         c = 0;
-        d = dN; g = gN;
-        dN = d + c_.dstep; gN = g + c_.gstep;
-        if (dN >= c_.Ds) { dN -= c_.Ds; ++gN; }
-        eoff = (unsigned)d * c_.sa + (unsigned)g * c_.sg;
-        soff = (unsigned)g * c_.Zs;
+        const int dn = d + c_.dstep;
+        const bool w = dn >= c_.Ds;
+        d = w ? dn - c_.Ds : dn;
+        g += c_.gstep + (w ? 1 : 0);
+        eoff += c_.estep + (w ? c_.ewrap : 0u);
+        soff += c_.sstep + (w ? c_.Zs : 0u);
         cx = c_.cxt[d]; cy = c_.cyt[d * 32 + lane]; cz = c_.czt[d * ZW + warp];
         csum = __dadd_rn(__dadd_rn(cx, cy), cz);
+      } else {
+        ++c;
       }
     }
 
-    // ---- prefetch block t+1 (registers for rhs/sigt, cp.async into the exchange slots for boundary faces) ----
+    // the element after the current one (used when a prefetch crosses the element boundary)
+    const int dn_ = d + c_.dstep;
+    const bool wn = dn_ >= c_.Ds;
+    const int dN = wn ? dn_ - c_.Ds : dn_, gN = g + c_.gstep + (wn ? 1 : 0);
+    const unsigned eoffN = eoff + c_.estep + (wn ? c_.ewrap : 0u), soffN = soff + c_.sstep + (wn ? c_.Zs : 0u);
+
+    // ---- prefetch block t+1 into registers ----
     if (pre) {
-      int cn = c + 1, dn = d, gn = g;
-      unsigned eoffn = eoff, soffn = soff;
-      if (!act || cn == nb) {
-        cn = 0; dn = dN; gn = gN;
-        eoffn = (unsigned)dn * c_.sa + (unsigned)gn * c_.sg;
-        soffn = (unsigned)gn * c_.Zs;
-        finn = c_.i_zero ? 0.0 : c_.ipl[(unsigned)dn * c_.ipd + (unsigned)gn * c_.ipg + c_.ip_idx];
-      }
-      const unsigned i0n = FWD ? 4u * cn : (unsigned)(ni - 4 - 4 * cn);
-      if (!(c_.exp & 4)) ldg256_nc(c_.rhs_b + (eoffn + c_.row_off + i0n), r4n);
-      if (!(c_.exp & 1)) ldg256_nc(c_.sigt_b + (soffn + c_.row_off + i0n), s4n);
+      const bool last = (c == nb - 1);
+      const int c1 = last ? 0 : c + 1;
+      const unsigned i0n = FWD ? 4u * c1 : (unsigned)(ni - 4 - 4 * c1);
+      if (!(c_.exp & 4)) ldg256_nc(c_.rhs_b + ((last ? eoffN : eoff) + c_.row_off + i0n), r4n);
+      if (!(c_.exp & 1)) ldg256_nc(c_.sigt_b + ((last ? soffN : soff) + c_.row_off + i0n), s4n);
+      if (last) finn = c_.i_zero ? 0.0 : c_.ipl[(unsigned)dN * c_.ipd + (unsigned)gN * c_.ipg + c_.ip_idx];
     }
 
     // ---- tile-boundary faces of block t+2: cp.async into a 3-slot ring (waited for one macro-step later) ----
-    if (c_.line_ok && (unsigned)(t + 2) < (unsigned)c_.T) {
-      const unsigned i0f = FWD ? 4u * cF : (unsigned)(ni - 4 - 4 * cF);
-      if (c_.j_first && !c_.j_zero) {
-        const double *src = c_.jpl + ((unsigned)dF * c_.jpd + (unsigned)gF * c_.jpg + c_.jp_row + i0f);
+    if (pre2 && (bnd_j || bnd_k)) {
+      const int cb = (t >= 0 ? c : nb + t) + 2;  // block index relative to the current (or virtual) element
+      const bool nxt = cb >= nb;
+      const int c2 = nxt ? cb - nb : cb;
+      const int dB = nxt ? dN : d, gB = nxt ? gN : g;
+      const unsigned i0f = FWD ? 4u * c2 : (unsigned)(ni - 4 - 4 * c2);
+      if (bnd_j) {
+        const double *src = c_.jpl + ((unsigned)dB * c_.jpd + (unsigned)gB * c_.jpg + c_.jp_row + i0f);
         cp_async16(c_.fjx + ring * (2 * JS) + threadIdx.x, src);
         cp_async16(c_.fjx + ring * (2 * JS) + JS + threadIdx.x, src + 2);
       }
-      if (c_.k_first && !c_.k_zero) {
-        const double *src = c_.kpl + ((unsigned)dF * c_.kpd + (unsigned)gF * c_.kpg + c_.kp_row + i0f);
+      if (bnd_k) {
+        const double *src = c_.kpl + ((unsigned)dB * c_.kpd + (unsigned)gB * c_.kpg + c_.kp_row + i0f);
         cp_async16(c_.fkin + ring * (2 * JS) + threadIdx.x, src);
         cp_async16(c_.fkin + ring * (2 * JS) + JS + threadIdx.x, src + 2);
-      }
-      if (++cF == nb) {
-        cF = 0;
-        dF += c_.dstep; gF += c_.gstep;
-        if (dF >= c_.Ds) { dF -= c_.Ds; ++gF; }
       }
     }
     cp_async_commit();
     const int rcur = (ring == 2) ? 0 : ring + 1;  // H mod 3: the slot fetched two macro-steps ago
 
-    // ---- incoming faces of block t: j from the previous lane (shuffle) or the tile boundary slot,
-    //      k from the previous warp's slot (tile boundary: filled by cp.async one macro-step ago) ----
+    // ---- incoming faces of block t: j from the previous lane (shuffle) or the tile boundary ring,
+    //      k from the previous warp's exchange slot or the tile boundary ring ----
     double fj[4], fk[4];
     {
       double sj[4];
@@ -329,8 +338,16 @@ __global__ void __launch_bounds__(ZW * 32, 1) sweep_zline_kernel(const kb200_swe
   const int cnt0 = (stream0 < E) ? (E - stream0 + nstreams - 1) / nstreams : 0;
   c.Hend = cnt0 * nb + (tjn - 1) + (tkn - 1);
   c.jjkk = jj + kk;
-  c.g0 = stream / Ds; c.d0 = stream - c.g0 * Ds;
   c.gstep = nstreams / Ds; c.dstep = nstreams - c.gstep * Ds;
+  {
+    const int g0 = stream / Ds, d0 = stream - g0 * Ds;  // first element; its virtual predecessor is one stream stride back
+    int dv = d0 - c.dstep, gv = g0 - c.gstep;
+    if (dv < 0) { dv += Ds; gv -= 1; }
+    c.dv = dv; c.gv = gv;
+  }
+  c.estep = (unsigned)c.dstep * c.sa + (unsigned)c.gstep * c.sg;
+  c.ewrap = c.sg - (unsigned)Ds * c.sa;
+  c.sstep = (unsigned)c.gstep * c.Zs;
 
   if (ds.id > 0) zline_run<EXACT, true>(c);
   else zline_run<EXACT, false>(c);
@@ -350,7 +367,7 @@ static int pow2_ceil(int v, int cap) {
 int kb200_sweep_zline_try(const kb200_sweep_desc *h, int n, const void *d_descs, cudaStream_t st) {
   const int layout = h[0].layout;
   if (layout != 0 && layout != 2) return -1;
-  if (h[0].ni % 4 != 0) return -1;
+  if (h[0].ni % 4 != 0 || h[0].ni < 8) return -1;
   const char *env = getenv("KB200_SWEEP_GENERIC");
   if (env && env[0] == '1') return -1;
   for (int i = 0; i < n; ++i) {
