@@ -206,17 +206,25 @@ __device__ __forceinline__ void zline_run(const ZCtx &cx_) {
           num = __dadd_rn(num, __dmul_rn(fj[m], cy));
           num = __dadd_rn(num, __dmul_rn(fk[m], cz));
           p = __ddiv_rn(num, den);
+          const double p2 = 2.0 * p;
+          fi = p2 - fi;
+          p4[m] = p; oj[m] = p2 - fj[m]; ok[m] = p2 - fk[m];
         } else {
-          const double rc = __drcp_rn(den);
+          // default arithmetic: psi = fi*A + B with A = cx/den, B = (rhs + fj*cy + fk*cz)/den and the
+          // outgoing i face fi' = fi*(2A-1) + 2B, so the recurrence along i is ONE dependent DFMA per
+          // zone; everything else (reciprocal by Newton from MUFU.RCP64H, A, B) is off the chain.
+          double y;
+          asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+          double e = fma(-den, y, 1.0);
+          y = fma(y, e, y);
+          e = fma(-den, y, 1.0);
+          const double rc = fma(y, e, y);
           const double part = fma(fk[m], cz, fma(fj[m], cy, r4[m]));
-          const double num = fma(fi, cxu, part);
-          const double q = num * rc;
-          const double rem = fma(-den, q, num);
-          p = fma(rem, rc, q);
+          const double A = cxu * rc, B = part * rc;
+          p = fma(fi, A, B);
+          fi = fma(fi, fma(2.0, A, -1.0), B + B);
+          p4[m] = p; oj[m] = fma(2.0, p, -fj[m]); ok[m] = fma(2.0, p, -fk[m]);
         }
-        const double p2 = 2.0 * p;
-        fi = p2 - fi;
-        p4[m] = p; oj[m] = p2 - fj[m]; ok[m] = p2 - fk[m];
       }
       if (!(c_.exp & 2)) stg256(c_.psi_b + (eoff + c_.row_off + i0), p4);
       if (c == nb - 1) {
