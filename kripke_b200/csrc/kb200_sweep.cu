@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_tile_kernel(const kb20
 using namespace kb200;
 
 int kb200_sweep_zline_try(const kb200_sweep_desc *h, int n, const void *d_descs, cudaStream_t st);  // kb200_sweep_zline.cu
+int kb200_sweep_elem_try(const kb200_sweep_desc *h, int n, const void *d_descs, cudaStream_t st);   // kb200_sweep_elem.cu
 
 extern "C" int kb200_sweep(const kb200_sweep_desc *h, int n, kb200_stream_t stream) {
   if (n <= 0) return 0;
@@ -189,6 +190,8 @@ extern "C" int kb200_sweep(const kb200_sweep_desc *h, int n, kb200_stream_t stre
   int rc = device_descs(h, sizeof(*h) * n, &d, st);
   if (rc) return rc;
   rc = kb200_sweep_zline_try(h, n, d, st);  // zone-fastest layouts with ni % 4 == 0
+  if (rc >= 0) return rc;
+  rc = kb200_sweep_elem_try(h, n, d, st);  // element-fastest layouts
   if (rc >= 0) return rc;
   SweepGeom gm;
   gm.layout = h[0].layout; gm.Ds = h[0].Ds; gm.Gs = h[0].Gs; gm.ni = h[0].ni; gm.nj = h[0].nj; gm.nk = h[0].nk;

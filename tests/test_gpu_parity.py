@@ -141,11 +141,12 @@ ZLINE_CASES = [
     "--zones 8,8,4 --groups 6 --quad 24 --legendre 1 --gset 1 --dset 8 --zset 1,1,1",      # packed sub-streams
     "--zones 32,16,48 --groups 4 --quad 16 --legendre 1 --gset 2 --dset 8 --zset 2,1,3",   # decomposed, 16^3 subdomains
     "--zones 4,33,17 --groups 3 --quad 8 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",     # one-lane / one-warp tiles
+    "--zones 16,12,20 --groups 8 --quad 48 --legendre 1 --gset 1 --dset 8 --zset 1,1,1",   # 48 elements: two 32-element slices
 ]
 
 
 @pytest.mark.parametrize("exact", [False, True])
-@pytest.mark.parametrize("layout", ["DGZ", "GDZ"])
+@pytest.mark.parametrize("layout", LAYOUTS)  # DGZ/GDZ: kb200_sweep_zline.cu; the other four: kb200_sweep_elem.cu
 @pytest.mark.parametrize("case", range(len(ZLINE_CASES)))
 def test_sweep_zone_fastest_line_kernel(gpu, case, layout, exact):
     gpu.abi().kb200_set_exact(int(exact))
