@@ -170,6 +170,9 @@ using namespace kb200;
 
 int kb200_sweep_zline_try(const kb200_sweep_desc *h, int n, const void *d_descs, cudaStream_t st);  // kb200_sweep_zline.cu
 int kb200_sweep_elem_try(const kb200_sweep_desc *h, int n, const void *d_descs, cudaStream_t st);   // kb200_sweep_elem.cu
+int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, const double *const *d_pop_w,
+                         const double *const *d_pop_vol, double *d_pop_partial, int pop_capacity, int *pop_count,
+                         cudaStream_t st);  // kb200_sweep_irow.cu
 
 extern "C" int kb200_sweep(const kb200_sweep_desc *h, int n, kb200_stream_t stream) {
   if (n <= 0) return 0;
@@ -189,6 +192,8 @@ extern "C" int kb200_sweep(const kb200_sweep_desc *h, int n, kb200_stream_t stre
   const void *d = nullptr;
   int rc = device_descs(h, sizeof(*h) * n, &d, st);
   if (rc) return rc;
+  rc = kb200_sweep_irow_try(h, n, d, nullptr, nullptr, nullptr, 0, nullptr, st);  // zone-fastest layouts, ni = 4 * 2^k, default arithmetic
+  if (rc >= 0) return rc;
   rc = kb200_sweep_zline_try(h, n, d, st);  // zone-fastest layouts with ni % 4 == 0
   if (rc >= 0) return rc;
   rc = kb200_sweep_elem_try(h, n, d, st);  // element-fastest layouts

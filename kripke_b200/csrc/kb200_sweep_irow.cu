@@ -1,0 +1,533 @@
+// SweepSubdomain for the zone-fastest storage orders (DGZ, GDZ) on sm_100a, default arithmetic:
+// i-rows across lanes, the i recurrence as a warp-level affine scan, k-planes as a warp pipeline.
+//
+// Reference arithmetic: src/Kripke/Kernel/SweepSubdomain.cpp:86-108.  With A = cx/den and
+// B = (rhs + fj*cy + fk*cz)/den the update of one zone is  psi = fi*A + B,  fi' = 2*psi - fi
+// = fi*(2A-1) + 2B : along i the face flux obeys an AFFINE recurrence whose coefficients do not
+// depend on fi.  Affine maps compose associatively, so a whole i-row can be advanced by a
+// log-depth scan instead of ni dependent steps.  That turns the memory-unfriendly mapping of
+// kb200_sweep_zline.cu (one thread per i-row, 32 different rows per request) into the natural one:
+//   * LR = ni/4 consecutive lanes hold one i-row of one phase-space element (d,g), four zones per
+//     lane: rhs, sigt and psi move as fully coalesced 256-bit accesses (ni*8 contiguous bytes per
+//     row); a warp carries ER = 32/LR rows of ER different elements;
+//   * a warp walks j = 0..nj-1 of ONE k-plane, so the j-face flux of a row is simply the
+//     register copy left by the previous step of the same lane (no shuffle, no memory);
+//   * the NW warps of a CTA hold NW consecutive k-planes.  Warp w hands the k-face flux of a row
+//     to warp w+1 through a small shared-memory ring guarded by mbarriers (full/empty per slot).
+//     There is NO CTA-wide barrier in the loop: the planes settle into a skewed pipeline on their
+//     own, and a late load stalls one warp instead of all of them.  k tiles (nk > NW) and
+//     elements follow each other in the same CTA without draining the pipeline; tile-boundary k
+//     faces go through the k_plane array (the last warp publishes a row counter, warp 0 waits on it);
+//   * inside a row: the reciprocals and the "A" half of every zone's map are computed BEFORE the
+//     warp waits for its upwind k faces; then each lane composes its four zone maps, a
+//     Kogge-Stone scan over the LR lanes (log2(LR) steps of 64-bit shuffles) gives every lane its
+//     incoming i-face flux, and the four zones are finished locally;
+//   * everything a row needs from global memory (rhs, sigt, incoming i face, tile-boundary k
+//     faces) is brought in IROW_PD row steps ahead by cp.async into a per-warp staging ring
+//     (each lane reads back only what it copied itself: no barrier, no registers held by loads).
+// The scan re-associates the i recurrence and 2*cos/delta is formed as (2*cos)*(1/delta), so
+// results differ from the reference in the last bits (|difference| ~ 1e-16 relative; contractions
+// |2A-1| < 1 keep the recurrence stable).  EXACT mode and shapes this kernel does not cover use
+// kb200_sweep_zline.cu / kb200_sweep.cu.
+// When pop_partial is non-null the kernel also accumulates Kernel::population's sum
+// (w(d)*psi)*volume(z) (src/Kripke/Kernel/Population.cpp:49-63) while psi is still in registers.
+#include "kb200_common.cuh"
+
+namespace kb200 {
+
+constexpr int IROW_RING = 2;   // slots of the k-face ring between neighbouring warps
+constexpr int IROW_PD = 2;     // prefetch distance in row steps
+constexpr int IROW_NS = IROW_PD + 1;  // staging slots per warp
+constexpr int IROW_MAXW = 16, IROW_MAXT = IROW_MAXW * 32;  // warps per CTA: up to 128 registers per thread
+// per warp and staging slot: rhs [2][32] double2, sigt [2][32] double2, incoming i face [32] double
+constexpr int IROW_STAGE_BYTES = 1024 + 1024 + 256;
+
+struct IGeom {  // kernel parameter: lives in the constant bank, costs no registers
+  int layout, Ds, Gs, ni, nj, nk;
+  int NW, nkt;  // warps (= k-planes) per CTA, k tiles
+  int E, ngroups;
+  unsigned sa, sg, Zs, ipd, ipg, jpd, jpg, kpd, kpg;  // element strides: psi/rhs (direction, group), zones, planes
+};
+
+__device__ __forceinline__ void ir_ldg256_nc(const double *p, double (&v)[4]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ir_ldg256_cg(const double *p, double (&v)[4]) {
+  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void ir_stg256(double *p, const double (&v)[4]) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+__device__ __forceinline__ unsigned ir_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ir_cp_async16(unsigned smem_dst, const void *gsrc, int src_size) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_size) : "memory");
+}
+__device__ __forceinline__ void ir_cp_async8(unsigned smem_dst, const void *gsrc, int src_size) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_size) : "memory");
+}
+__device__ __forceinline__ void ir_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ir_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ double2 ir_lds128(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ir_lds64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ir_sts128(unsigned addr, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void ir_st_release(unsigned addr, unsigned v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// spin until the counter at `addr` has reached `target` (acquire at CTA scope; the counter only grows)
+__device__ __forceinline__ void ir_wait_ge(unsigned addr, unsigned target) {
+  unsigned v;
+  do {
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  } while ((int)(v - target) < 0);
+}
+__device__ __forceinline__ void ir_mb_init(unsigned addr, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ir_mb_arrive(unsigned addr) {  // release at CTA scope, no fence instruction
+  asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void ir_mb_wait(unsigned addr, unsigned parity) {  // acquire at CTA scope, hardware-assisted wait
+  asm volatile("{\n .reg .pred p;\n IRW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra IRW;\n}" ::"r"(addr), "r"(parity) : "memory");
+}
+
+struct IShared {  // shared-window addresses of the pieces of dynamic shared memory
+  unsigned fkx;          // [IROW_RING][NW+1][2][32] double2: k-face exchange ring (entry 0 of a slot row is unused)
+  unsigned kin;          // [IROW_NS][2][32] double2: warp 0's tile-boundary k faces
+  unsigned stage;        // [NW][IROW_NS] staging slots of IROW_STAGE_BYTES
+  unsigned full, empty;  // [NW+1][IROW_RING] mbarriers of the ring slots (32 arrivals each)
+  unsigned prod;         // [1] rows whose tile-boundary k faces the last warp has put into k_plane
+  const double *cxt, *txc, *tyc, *tzc, *rdy, *rdz;  // [Ds] 2*xcos/dx[0], 2*xcos, 2*ycos, 2*zcos ; [nj] 1/dy ; [nk] 1/dz
+};
+
+// What a warp needs to know about one stream item = (element group, k tile): ER elements in one k-plane.
+struct IItem {
+  int d, g;                    // phase-space element of this lane's segment
+  bool ev, kv;                 // segment holds a real element; this warp's k-plane exists in the tile
+  int kz;                      // memory k index of the plane
+  unsigned off0, soff0, ipx0;  // element offsets of the item's first row: rhs/psi block, sigt block, i_plane entry
+  unsigned kpx0;               // k_plane block of the first row (warp 0 only)
+};
+
+template <int LR>
+__device__ __forceinline__ IItem irow_item(const IGeom &gm, int gi, int t, int w, int seg, unsigned i0, int jd, int kd) {
+  constexpr int ER = 32 / LR;
+  IItem it;
+  const int e = gi * ER + seg;
+  it.ev = e < gm.E;
+  const int ee = it.ev ? e : gm.E - 1;  // idle segments shadow a valid element (loads stay in bounds, stores are masked)
+  it.g = ee / gm.Ds;
+  it.d = ee - it.g * gm.Ds;
+  const int kl = t * gm.NW + w;
+  it.kv = kl < gm.nk;
+  const int klc = it.kv ? kl : gm.nk - 1;
+  it.kz = (kd > 0) ? klc : gm.nk - 1 - klc;
+  const int jz0 = (jd > 0) ? 0 : gm.nj - 1;
+  const unsigned zoff = (unsigned)((it.kz * gm.nj + jz0) * gm.ni) + i0;
+  it.off0 = (unsigned)it.d * gm.sa + (unsigned)it.g * gm.sg + zoff;
+  it.soff0 = (unsigned)it.g * gm.Zs + zoff;
+  it.ipx0 = (unsigned)it.d * gm.ipd + (unsigned)it.g * gm.ipg + (unsigned)(it.kz * gm.nj + jz0);
+  it.kpx0 = (unsigned)it.d * gm.kpd + (unsigned)it.g * gm.kpg + (unsigned)(jz0 * gm.ni) + i0;
+  return it;
+}
+
+template <int LR, bool FWD, bool UNI, bool POP>
+__device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGeom &gm, const IShared &sh,
+                                           const double *__restrict__ wq, const double *__restrict__ vol) {
+  constexpr int R = IROW_RING, PD = IROW_PD, NS = IROW_NS;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int seg = lane / LR, ls = lane % LR;
+  const int NW = gm.NW, ni = gm.ni, nj = gm.nj, nk = gm.nk, nkt = gm.nkt;
+  const unsigned i0 = FWD ? 4u * ls : (unsigned)(ni - 4 - 4 * ls);  // memory position of this lane's four zones
+  const int jd = ds.jd, kd = ds.kd;
+  const bool i_zero = ds.inflow_zero[0] != 0, j_zero = ds.inflow_zero[1] != 0, k_zero = ds.inflow_zero[2] != 0;
+  const int jstep = (jd > 0) ? ni : -ni;
+  const int gstride = (int)gridDim.x;
+
+  const unsigned stage0 = sh.stage + (unsigned)(w * NS) * IROW_STAGE_BYTES + 16u * lane;  // + slot * IROW_STAGE_BYTES
+  const unsigned kin0 = sh.kin + 16u * lane;                                               // + slot * 1024 (warp 0)
+  const unsigned fk_in0 = sh.fkx + (unsigned)w * 1024u + 16u * lane;                       // + ring slot * (NW+1)*1024
+  const unsigned fkx_slot = (unsigned)(NW + 1) * 1024u;
+  const unsigned full_in = sh.full + 8u * (unsigned)(w * R), full_out = full_in + 8u * R;
+  const unsigned empty_in = sh.empty + 8u * (unsigned)(w * R), empty_out = empty_in + 8u * R;
+
+  double pop = 0.0;
+  double fj[4] = {0, 0, 0, 0};
+  int gi = (int)blockIdx.x, t = 0;
+  const bool any = gi < gm.ngroups;
+  IItem nx = irow_item<LR>(gm, any ? gi : 0, 0, w, seg, i0, jd, kd);
+  bool nx_ok = any;   // the item `nx` exists
+  unsigned q = 0;     // row steps done by this warp
+  unsigned slot = 0;  // q % R
+  unsigned ph = 0;    // (q / R) & 1: phase parity of the ring slot's current use
+  unsigned sq = 0;    // q % NS: staging slot of the current row
+
+  // Loads of row `r` (0-based in item `it`, r < nj) whose step is qn: rhs, sigt, the i-face flux and, for
+  // warp 0, the tile-boundary k faces.  All by cp.async; each lane reads back only what it copied itself.
+  auto prefetch = [&](const IItem &it, int r, bool ktile0, unsigned qn, unsigned sqn) {
+    const unsigned st = stage0 + sqn * IROW_STAGE_BYTES;
+    const unsigned roff = (unsigned)(r * jstep);
+    const double *rp = ds.rhs + (it.off0 + roff), *sp = ds.sigt + (it.soff0 + roff);
+    ir_cp_async16(st, rp, 16); ir_cp_async16(st + 512, rp + 2, 16);
+    ir_cp_async16(st + 1024, sp, 16); ir_cp_async16(st + 1536, sp + 2, 16);
+    ir_cp_async8(st + 2048 - 8u * lane, ds.i_plane + (it.ipx0 + (unsigned)(r * jd)), i_zero ? 0 : 8);
+    if (w == 0) {
+      // rows of a later k tile were written by the tile's predecessor nj row steps earlier
+      if (!ktile0) ir_wait_ge(sh.prod, qn + 1u - (unsigned)nj);
+      const double *src = ds.k_plane + (it.kpx0 + roff);
+      const int sz = (k_zero && ktile0) ? 0 : 16;  // vacuum: zero fill
+      const unsigned dst = kin0 + sqn * 1024u;
+      ir_cp_async16(dst, src, sz);
+      ir_cp_async16(dst + 512, src + 2, sz);
+    }
+  };
+  auto next_sq = [](unsigned s, int by) { unsigned v = s + (unsigned)by; return v >= (unsigned)NS ? v - NS : v; };
+
+  // prologue: rows 0..PD-1 of the first item, one cp.async group per row
+#pragma unroll
+  for (int r = 0; r < PD; ++r) {
+    if (nx_ok && nx.kv && r < nj) prefetch(nx, r, true, (unsigned)r, (unsigned)r);
+    ir_cp_async_commit();
+  }
+
+  while (nx_ok) {
+    const IItem it = nx;
+    const bool ktile0 = (t == 0);
+    // the item after this one
+    int ngi = gi, nt = t + 1;
+    if (nt == nkt) { nt = 0; ngi += gstride; }
+    nx_ok = ngi < gm.ngroups;
+    nx = irow_item<LR>(gm, nx_ok ? ngi : gi, nt, w, seg, i0, jd, kd);
+    const bool nx_pre = nx_ok && nx.kv;
+
+    if (!it.kv) {  // this warp's plane does not exist in the (short) last k tile: only keep the ring handshakes going
+      for (int j = 0; j < nj; ++j) {
+        if (w > 0) { ir_mb_wait(full_in + 8u * slot, ph); ir_mb_arrive(empty_in + 8u * slot); }
+        if (w < NW - 1) {
+          if (q >= (unsigned)R) ir_mb_wait(empty_out + 8u * slot, ph ^ 1u);
+          ir_mb_arrive(full_out + 8u * slot);
+        }
+        ++q;
+        sq = next_sq(sq, 1);
+        if (++slot == R) { slot = 0; ph ^= 1u; }
+      }
+      ir_cp_async_wait<0>();
+#pragma unroll
+      for (int r = 0; r < PD; ++r) {  // the next item (tile 0 of the next group) starts from scratch
+        if (nx_pre && r < nj) prefetch(nx, r, nt == 0, q + (unsigned)r, next_sq(sq, r));
+        ir_cp_async_commit();
+      }
+      gi = ngi; t = nt;
+      continue;
+    }
+
+    const int kl = t * NW + w;
+    const bool k_out_global = (kl == nk - 1) || (w == NW - 1);
+    const double cx = sh.cxt[it.d], cz = sh.tzc[it.d] * sh.rdz[it.kz], tyc = sh.tyc[it.d];
+    unsigned off = it.off0, ipx = it.ipx0;
+    int jz = (jd > 0) ? 0 : nj - 1;
+
+#pragma unroll 1
+    for (int j = 0; j < nj; ++j) {
+      // ---- loads of the row PD steps ahead ----
+      {
+        const int r = j + PD;
+        const unsigned sqn = next_sq(sq, PD);
+        if (r < nj) prefetch(it, r, ktile0, q + (unsigned)PD, sqn);
+        else if (nx_pre && r - nj < nj) prefetch(nx, r - nj, nt == 0, q + (unsigned)PD, sqn);
+      }
+      ir_cp_async_commit();
+      ir_cp_async_wait<PD>();  // the copies issued PD steps ago for this row have landed
+
+      // ---- everything that does not need the upwind k and j faces ----
+      const unsigned st = stage0 + sq * IROW_STAGE_BYTES;
+      double A[4], rc[4], r4[4];
+      const double cy = tyc * sh.rdy[jz];
+      {
+        const double2 e = ir_lds128(st + 1024), f = ir_lds128(st + 1536);
+        const double s4[4] = {e.x, e.y, f.x, f.y};
+        const double2 a = ir_lds128(st), b = ir_lds128(st + 512);
+        r4[0] = a.x; r4[1] = a.y; r4[2] = b.x; r4[3] = b.y;
+        const double csum = __dadd_rn(__dadd_rn(cx, cy), cz);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // u = position in sweep order, m = memory slot
+          const int m = FWD ? u : 3 - u;
+          double cxu = cx, cs = csum;
+          if (!UNI) {
+            cxu = __ddiv_rn(sh.txc[it.d], ds.dx[i0 + m]);
+            cs = __dadd_rn(__dadd_rn(cxu, cy), cz);
+          }
+          const double den = __dadd_rn(cs, s4[m]);
+          double y;
+          asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+          const double e1 = fma(-den, y, 1.0);  // cubic step: y*(1 + e + e^2), e ~ 2^-23 -> error ~ 2^-69
+          const double e2 = fma(e1, e1, e1);
+          rc[u] = fma(y, e2, y);
+          A[u] = cxu * rc[u];
+        }
+      }
+      const double fi0 = ir_lds64(st + 2048 - 8u * lane);
+      if (j == 0) {
+        if (j_zero) { fj[0] = fj[1] = fj[2] = fj[3] = 0.0; }
+        else ir_ldg256_cg(ds.j_plane + ((unsigned)it.d * gm.jpd + (unsigned)it.g * gm.jpg + (unsigned)(it.kz * ni) + i0), fj);
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) r4[m] = fma(fj[m], cy, r4[m]);  // rhs + fj*cy
+
+      // ---- upwind k faces: from warp w-1 through the ring, or (warp 0) from the staged k_plane row ----
+      double fk[4];
+      {
+        unsigned src = fk_in0 + slot * fkx_slot;
+        if (w > 0) ir_mb_wait(full_in + 8u * slot, ph);
+        else src = kin0 + sq * 1024u;
+        const double2 k0 = ir_lds128(src), k1 = ir_lds128(src + 512);
+        fk[0] = k0.x; fk[1] = k0.y; fk[2] = k1.x; fk[3] = k1.y;
+        if (w > 0) ir_mb_arrive(empty_in + 8u * slot);  // the slot may be refilled
+      }
+      // B = (rhs + fj*cy + fk*cz) / den ; this lane's composite map  fi_out = al * fi_in + be
+      double B[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int m = FWD ? u : 3 - u;
+        B[u] = fma(fk[m], cz, r4[m]) * rc[u];
+      }
+      double al = fma(2.0, A[0], -1.0), be = B[0] + B[0];
+#pragma unroll
+      for (int u = 1; u < 4; ++u) {
+        const double a = fma(2.0, A[u], -1.0);
+        be = fma(a, be, B[u] + B[u]);
+        al *= a;
+      }
+      // inclusive scan over the LR lanes of the row
+#pragma unroll
+      for (int dlt = 1; dlt < LR; dlt <<= 1) {
+        const double alp = __shfl_up_sync(0xffffffffu, al, dlt, LR);
+        const double bep = __shfl_up_sync(0xffffffffu, be, dlt, LR);
+        if (ls >= dlt) {
+          be = fma(al, bep, be);
+          al *= alp;
+        }
+      }
+      const double fo = fma(al, fi0, be);  // outgoing i face of this lane's last zone
+      double fi = fi0;
+      if (LR > 1) {
+        const double fprev = __shfl_up_sync(0xffffffffu, fo, 1, LR);
+        if (ls > 0) fi = fprev;
+      }
+      double p4[4], ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int m = FWD ? u : 3 - u;
+        const double p = fma(fi, A[u], B[u]);
+        p4[m] = p;
+        fi = fma(2.0, p, -fi);
+        fj[m] = fma(2.0, p, -fj[m]);
+        ok[m] = fma(2.0, p, -fk[m]);
+      }
+      if (w < NW - 1) {  // (the last plane of a short tile publishes too: idle warps keep shaking hands)
+        if (q >= (unsigned)R) ir_mb_wait(empty_out + 8u * slot, ph ^ 1u);  // warp w+1 has emptied this ring slot
+        const unsigned dst = fk_in0 + slot * fkx_slot + 1024u;
+        ir_sts128(dst, ok[0], ok[1]);
+        ir_sts128(dst + 512, ok[2], ok[3]);
+        ir_mb_arrive(full_out + 8u * slot);
+      }
+      if (it.ev) {
+        ir_stg256(ds.psi + off, p4);
+        if (POP) {
+          double v4[4];
+          ir_ldg256_nc(vol + ((unsigned)((it.kz * nj + jz) * ni) + i0), v4);
+          const double wd = wq[it.d];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pop = fma(wd * p4[u], v4[u], pop);
+        }
+        if (ls == LR - 1) {
+          ds.i_plane[ipx] = fo;
+          if (ds.out_plane[0]) ds.out_plane[0][ipx] = fo;
+        }
+        if (j == nj - 1) {
+          const unsigned jpx = (unsigned)it.d * gm.jpd + (unsigned)it.g * gm.jpg + (unsigned)(it.kz * ni) + i0;
+          ir_stg256(ds.j_plane + jpx, fj);
+          if (ds.out_plane[1]) ir_stg256(ds.out_plane[1] + jpx, fj);
+        }
+        if (k_out_global) {
+          const unsigned kpx = it.kpx0 + (unsigned)(j * jstep);
+          ir_stg256(ds.k_plane + kpx, ok);
+          if (kl == nk - 1 && ds.out_plane[2]) ir_stg256(ds.out_plane[2] + kpx, ok);
+        }
+      }
+      if (w == NW - 1 && nkt > 1) {  // tile-boundary k faces are in k_plane: tell warp 0
+        __syncwarp();
+        if (lane == 0) ir_st_release(sh.prod, q + 1u);
+      }
+      ++q;
+      sq = next_sq(sq, 1);
+      if (++slot == R) { slot = 0; ph ^= 1u; }
+      off += (unsigned)jstep; ipx += (unsigned)jd; jz += jd;
+    }
+    gi = ngi; t = nt;
+  }
+  ir_cp_async_wait<0>();
+  return pop;
+}
+
+template <int LR, bool POP>
+__global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sweep_desc *__restrict__ descs, const __grid_constant__ IGeom gm,
+                                                             const double *const *__restrict__ pop_w,
+                                                             const double *const *__restrict__ pop_vol,
+                                                             double *__restrict__ pop_partial) {
+  extern __shared__ __align__(16) unsigned char ism[];
+  __shared__ kb200_sweep_desc ds;  // the descriptor is read all the time: keep it one LDS away
+  if (threadIdx.x < sizeof(kb200_sweep_desc) / sizeof(int))
+    reinterpret_cast<int *>(&ds)[threadIdx.x] = reinterpret_cast<const int *>(&descs[blockIdx.y])[threadIdx.x];
+  __syncthreads();
+  const int Ds = gm.Ds, nj = gm.nj, nk = gm.nk, NW = gm.NW;
+  IShared sh;
+  unsigned char *p = ism;
+  sh.fkx = ir_smem_addr(p); p += (size_t)IROW_RING * (NW + 1) * 1024;
+  sh.kin = ir_smem_addr(p); p += (size_t)IROW_NS * 1024;
+  sh.stage = ir_smem_addr(p); p += (size_t)NW * IROW_NS * IROW_STAGE_BYTES;
+  double *tab = reinterpret_cast<double *>(p);
+  double *cxt = tab, *txc = cxt + Ds, *tyc = txc + Ds, *tzc = tyc + Ds, *rdy = tzc + Ds, *rdz = rdy + nj;
+  double *red = rdz + nk;  // [32] block reduction of the population partials
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(red + 32);
+  sh.full = ir_smem_addr(bars);
+  sh.empty = sh.full + 8u * (unsigned)((NW + 1) * IROW_RING);
+  unsigned *prod = reinterpret_cast<unsigned *>(bars + 2 * (NW + 1) * IROW_RING);
+  sh.prod = ir_smem_addr(prod);
+  sh.cxt = cxt; sh.txc = txc; sh.tyc = tyc; sh.tzc = tzc; sh.rdy = rdy; sh.rdz = rdz;
+  if (threadIdx.x == 0) *prod = 0u;
+  if ((int)threadIdx.x < 2 * (NW + 1) * IROW_RING) ir_mb_init(sh.full + 8u * threadIdx.x, 32u);
+
+  // 2*cos tables and reciprocal zone widths (SweepSubdomain.cpp:88-93), indexed by the MEMORY zone index
+  for (int d = threadIdx.x; d < Ds; d += blockDim.x) {
+    const double t2 = 2.0 * ds.xcos[d];
+    txc[d] = t2;
+    cxt[d] = t2 / ds.dx[0];
+    tyc[d] = 2.0 * ds.ycos[d];
+    tzc[d] = 2.0 * ds.zcos[d];
+  }
+  for (int j = threadIdx.x; j < nj; j += blockDim.x) rdy[j] = 1.0 / ds.dy[j];
+  for (int k = threadIdx.x; k < nk; k += blockDim.x) rdz[k] = 1.0 / ds.dz[k];
+  int uni = 1;
+  for (int i = threadIdx.x; i < gm.ni; i += blockDim.x) uni &= (ds.dx[i] == ds.dx[0]);
+  const bool uniform_x = __syncthreads_and(uni) != 0;  // also orders the table writes and the mbarrier inits
+
+  const double *wq = POP ? pop_w[blockIdx.y] : nullptr;
+  const double *vol = POP ? pop_vol[blockIdx.y] : nullptr;
+  double pop;
+  if (uniform_x) {
+    if (ds.id > 0) pop = irow_run<LR, true, true, POP>(ds, gm, sh, wq, vol);
+    else pop = irow_run<LR, false, true, POP>(ds, gm, sh, wq, vol);
+  } else {
+    if (ds.id > 0) pop = irow_run<LR, true, false, POP>(ds, gm, sh, wq, vol);
+    else pop = irow_run<LR, false, false, POP>(ds, gm, sh, wq, vol);
+  }
+
+  if (POP) {  // fixed-order block reduction: lanes, then warps
+    pop = warp_sum(pop);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = pop;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < NW; ++i) t += red[i];
+      pop_partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+  }
+}
+
+}  // namespace kb200
+
+using namespace kb200;
+
+template <int LR>
+static int launch_irow(const kb200_sweep_desc *d_descs, int n, const IGeom &gm, int cps, size_t smem, const double *const *pw,
+                       const double *const *pv, double *pp, cudaStream_t st) {
+  dim3 grid(cps, n, 1);
+  if (pp) {
+    auto k = sweep_irow_kernel<LR, true>;
+    KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, pw, pv, pp);
+  } else {
+    auto k = sweep_irow_kernel<LR, false>;
+    KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, nullptr, nullptr, nullptr);
+  }
+  return post_launch("sweep_irow");
+}
+
+// Returns 0 if the batch was handled, -1 if this path does not apply (caller falls back), >0 on error.
+// pop_* (optional, device pointer tables of n entries + a scratch of pop_capacity doubles): fused population partials.
+int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, const double *const *d_pop_w,
+                         const double *const *d_pop_vol, double *d_pop_partial, int pop_capacity, int *pop_count,
+                         cudaStream_t st) {
+  const int layout = h[0].layout;
+  if (pop_count) *pop_count = 0;
+  if (layout != 0 && layout != 2) return -1;
+  if (exact_mode()) return -1;
+  const char *env = getenv("KB200_SWEEP_IROW");
+  if (env && env[0] == '0') return -1;
+  const int ni = h[0].ni, nj = h[0].nj, nk = h[0].nk;
+  if (ni % 4 != 0) return -1;
+  const int LR = ni / 4;
+  if (LR > 32 || (LR & (LR - 1)) != 0) return -1;
+  for (int i = 0; i < n; ++i) {
+    const void *ptrs[] = {h[i].rhs, h[i].psi, h[i].sigt, h[i].j_plane, h[i].k_plane, h[i].out_plane[1], h[i].out_plane[2]};
+    for (const void *p : ptrs)
+      if (((uintptr_t)p & 31) != 0) return -1;
+    if (((uintptr_t)h[i].i_plane & 7) != 0) return -1;
+  }
+  if ((double)h[0].Ds * h[0].Gs * ni * nj * nk >= 2147483648.0) return -1;  // 32-bit element offsets
+  IGeom gm;
+  gm.layout = layout; gm.Ds = h[0].Ds; gm.Gs = h[0].Gs; gm.ni = ni; gm.nj = nj; gm.nk = nk;
+  {
+    const long long Zs = (long long)ni * nj * nk;
+    const Strides3 fs = strides_dgz(layout, gm.Ds, gm.Gs, Zs);
+    const StridesP ips = strides_plane(layout, gm.Ds, gm.Gs, nj, nk), jps = strides_plane(layout, gm.Ds, gm.Gs, ni, nk),
+                   kps = strides_plane(layout, gm.Ds, gm.Gs, ni, nj);
+    gm.sa = (unsigned)fs.a; gm.sg = (unsigned)fs.g; gm.Zs = (unsigned)Zs;
+    gm.ipd = (unsigned)ips.d; gm.ipg = (unsigned)ips.g; gm.jpd = (unsigned)jps.d; gm.jpg = (unsigned)jps.g;
+    gm.kpd = (unsigned)kps.d; gm.kpg = (unsigned)kps.g;
+    gm.E = gm.Ds * gm.Gs;
+  }
+  gm.nkt = (nk + IROW_MAXW - 1) / IROW_MAXW;
+  gm.NW = (nk + gm.nkt - 1) / gm.nkt;
+  // rows are fetched IROW_PD steps ahead, at most into the next item; warp 0 must not wait for tile-boundary
+  // k faces of a row the last warp can only produce after warp 0 has moved on
+  if (nj <= IROW_PD) return -1;
+  const size_t smem = (size_t)IROW_RING * (gm.NW + 1) * 1024 + (size_t)IROW_NS * 1024 + (size_t)gm.NW * IROW_NS * IROW_STAGE_BYTES +
+                      ((size_t)4 * gm.Ds + nj + nk + 32 + 2 * (gm.NW + 1) * IROW_RING + 2) * sizeof(double);
+  if (smem > 226 * 1024) return -1;
+  const int ER = 32 / LR;
+  const int ngroups = (gm.Ds * gm.Gs + ER - 1) / ER;
+  gm.ngroups = ngroups;
+  int per_sm = (65536 / 128) / (gm.NW * 32);
+  const int by_smem = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > by_smem) per_sm = by_smem;
+  if (per_sm < 1) per_sm = 1;
+  int cps = (int)(((long long)sm_count() * per_sm) / n);
+  if (cps < 1) cps = 1;
+  if (cps > ngroups) cps = ngroups;
+  double *pp = d_pop_partial;
+  if (pp && (long long)cps * n > pop_capacity) pp = nullptr;
+  if (pop_count) *pop_count = pp ? cps * n : 0;
+  const kb200_sweep_desc *dd = (const kb200_sweep_desc *)d_descs;
+  switch (LR) {
+    case 1: return launch_irow<1>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st);
+    case 2: return launch_irow<2>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st);
+    case 4: return launch_irow<4>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st);
+    case 8: return launch_irow<8>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st);
+    case 16: return launch_irow<16>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st);
+    default: return launch_irow<32>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st);
+  }
+}

@@ -142,6 +142,11 @@ ZLINE_CASES = [
     "--zones 32,16,48 --groups 4 --quad 16 --legendre 1 --gset 2 --dset 8 --zset 2,1,3",   # decomposed, 16^3 subdomains
     "--zones 4,33,17 --groups 3 --quad 8 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",     # one-lane / one-warp tiles
     "--zones 16,12,20 --groups 8 --quad 48 --legendre 1 --gset 1 --dset 8 --zset 1,1,1",   # 48 elements: two 32-element slices
+    # default arithmetic on DGZ/GDZ with ni = 4 * 2^k takes the i-row scan kernel (kb200_sweep_irow.cu):
+    "--zones 16,40,44 --groups 3 --quad 16 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",   # nk > 32: two k tiles of 22 planes
+    "--zones 64,6,5 --groups 3 --quad 8 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",      # 16 lanes per row, odd element count
+    "--zones 128,4,3 --groups 2 --quad 8 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",     # one row per warp (32-lane scan)
+    "--zones 32,34,33 --groups 2 --quad 8 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",    # 8 lanes per row, k tiles 17+16
 ]
 
 
