@@ -285,6 +285,8 @@ using namespace kb200;
 
 int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, int nsets, int accumulate, const void *d_views,
                           int n, const void *const *h_ptrs, int n_ptrs, cudaStream_t st);  // kb200_moments_mma.cu
+int kb200_moments_rowmma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, int nsets, int accumulate, const void *d_views,
+                             int n, const void *const *h_ptrs, int n_ptrs, cudaStream_t st);  // kb200_moments_rowmma.cu
 
 namespace {
 
@@ -372,6 +374,8 @@ static int run_moments(int mode, int layout, int M, int Ds, int Gs, int Zs, int 
       for (int s = 0; s < (mode == 0 ? 1 : nsets); ++s) ptrs.push_back(tout[s]);
     }
     rc = kb200_moments_mma_try(mode, layout, M, Ds, Gs, Zs, nsets, accumulate, d_views, n, ptrs.data(), (int)ptrs.size(), st);
+    if (rc >= 0) return rc;
+    rc = kb200_moments_rowmma_try(mode, layout, M, Ds, Gs, Zs, nsets, accumulate, d_views, n, ptrs.data(), (int)ptrs.size(), st);
     if (rc >= 0) return rc;
   }
 

@@ -35,8 +35,8 @@
 
 namespace kb200 {
 
-constexpr int IROW_RING = 2;   // slots of the k-face ring between neighbouring warps
-constexpr int IROW_PD = 2;     // prefetch distance in row steps
+constexpr int IROW_RING = 3;   // slots of the k-face ring between neighbouring warps
+constexpr int IROW_PD = 3;     // prefetch distance in row steps
 constexpr int IROW_NS = IROW_PD + 1;  // staging slots per warp
 constexpr int IROW_MAXW = 16, IROW_MAXT = IROW_MAXW * 32;  // warps per CTA: up to 128 registers per thread
 // per warp and staging slot: rhs [2][32] double2, sigt [2][32] double2, incoming i face [32] double
