@@ -163,6 +163,16 @@ typedef struct {
   double *out_plane[3];
 } kb200_sweep_desc;
 int kb200_sweep(const kb200_sweep_desc *h_descs, int n, kb200_stream_t stream);
+/* Same sweep, and -- where the kernel in use supports it -- Kernel::population's sum over the n swept
+ * subdomains is accumulated while psi is still in registers (saves re-reading psi,
+ * 8 bytes per unknown).  h_w[i] / h_volume[i] are the DEVICE pointers of quadrature/w [Ds] and volume
+ * [Zs] of subdomain i.  On return *count doubles have been written to d_partials (capacity >= count is
+ * checked); their sum in index order is sum_i sum_{d,g,z} (w*psi)*volume.  *count == 0 means the fused
+ * path did not apply and only the sweep was done: the caller then uses kb200_population. */
+int kb200_sweep_population(const kb200_sweep_desc *h_descs, int n, const double *const *h_w, const double *const *h_volume,
+                           double *d_partials, int capacity, int *count, kb200_stream_t stream);
+/* *d_result = sum of d_partials[0..n) in index order (fixed-order tree, deterministic) */
+int kb200_population_reduce(const double *d_partials, int n, double *d_result, kb200_stream_t stream);
 
 /* ---- layout transform (remaining nestings via transform) --------------------------
  * Re-orders a 3-index field (a,b,c extents in canonical <Direction|Moment, Group, Zone> order)

@@ -297,6 +297,12 @@ int kb200_source(const kb200_source_desc *h, int n, kb200_stream_t stream) {
 
 size_t kb200_population_scratch_doubles(void) { return kPopMaxBlocks; }
 
+int kb200_population_reduce(const double *d_partials, int n, double *d_result, kb200_stream_t stream) {
+  KB_REQUIRE(d_result && (d_partials || n <= 0), "kb200_population_reduce: null pointer");
+  population_final_kernel<<<1, 256, 0, resolve_stream(stream)>>>(d_partials, n > 0 ? n : 0, d_result, 0);
+  return post_launch("population_final");
+}
+
 int kb200_population(const kb200_population_desc *h, int n, double *d_scratch, double *d_result, kb200_stream_t stream) {
   KB_REQUIRE(d_result && d_scratch, "kb200_population: null result/scratch");
   cudaStream_t st = resolve_stream(stream);

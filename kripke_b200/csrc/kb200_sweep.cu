@@ -174,7 +174,9 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
                          const double *const *d_pop_vol, double *d_pop_partial, int pop_capacity, int *pop_count,
                          cudaStream_t st);  // kb200_sweep_irow.cu
 
-extern "C" int kb200_sweep(const kb200_sweep_desc *h, int n, kb200_stream_t stream) {
+static int sweep_impl(const kb200_sweep_desc *h, int n, const double *const *h_w, const double *const *h_volume, double *d_partials,
+                      int capacity, int *count, kb200_stream_t stream) {
+  if (count) *count = 0;
   if (n <= 0) return 0;
   KB_REQUIRE(h, "kb200_sweep: null descriptors");
   for (int i = 0; i < n; ++i) {
@@ -192,8 +194,17 @@ extern "C" int kb200_sweep(const kb200_sweep_desc *h, int n, kb200_stream_t stre
   const void *d = nullptr;
   int rc = device_descs(h, sizeof(*h) * n, &d, st);
   if (rc) return rc;
-  rc = kb200_sweep_irow_try(h, n, d, nullptr, nullptr, nullptr, 0, nullptr, st);  // zone-fastest layouts, ni = 4 * 2^k, default arithmetic
-  if (rc >= 0) return rc;
+  {  // zone-fastest layouts, ni = 4 * 2^k, default arithmetic; optionally with fused population partials
+    const void *d_w = nullptr, *d_v = nullptr;
+    if (d_partials && h_w && h_volume && capacity > 0) {
+      rc = device_descs(h_w, sizeof(double *) * n, &d_w, st);
+      if (rc) return rc;
+      rc = device_descs(h_volume, sizeof(double *) * n, &d_v, st);
+      if (rc) return rc;
+    }
+    rc = kb200_sweep_irow_try(h, n, d, (const double *const *)d_w, (const double *const *)d_v, d_w ? d_partials : nullptr, capacity, count, st);
+    if (rc >= 0) return rc;
+  }
   rc = kb200_sweep_zline_try(h, n, d, st);  // zone-fastest layouts with ni % 4 == 0
   if (rc >= 0) return rc;
   rc = kb200_sweep_elem_try(h, n, d, st);  // element-fastest layouts
@@ -215,4 +226,14 @@ extern "C" int kb200_sweep(const kb200_sweep_desc *h, int n, kb200_stream_t stre
     if (rc) return rc;
   }
   return 0;
+}
+
+extern "C" int kb200_sweep(const kb200_sweep_desc *h, int n, kb200_stream_t stream) {
+  return sweep_impl(h, n, nullptr, nullptr, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int kb200_sweep_population(const kb200_sweep_desc *h, int n, const double *const *h_w, const double *const *h_volume,
+                                      double *d_partials, int capacity, int *count, kb200_stream_t stream) {
+  KB_REQUIRE(count, "kb200_sweep_population: null count");
+  return sweep_impl(h, n, h_w, h_volume, d_partials, capacity, count, stream);
 }

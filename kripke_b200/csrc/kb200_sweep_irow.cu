@@ -35,8 +35,8 @@
 
 namespace kb200 {
 
-constexpr int IROW_RING = 3;   // slots of the k-face ring between neighbouring warps
-constexpr int IROW_PD = 3;     // prefetch distance in row steps
+constexpr int IROW_RING = 2;   // slots of the k-face ring between neighbouring warps
+constexpr int IROW_PD = 2;     // prefetch distance in row steps
 constexpr int IROW_NS = IROW_PD + 1;  // staging slots per warp
 constexpr int IROW_MAXW = 16, IROW_MAXT = IROW_MAXW * 32;  // warps per CTA: up to 128 registers per thread
 // per warp and staging slot: rhs [2][32] double2, sigt [2][32] double2, incoming i face [32] double
@@ -146,6 +146,7 @@ template <int LR, bool FWD, bool UNI, bool POP>
 __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGeom &gm, const IShared &sh,
                                            const double *__restrict__ wq, const double *__restrict__ vol) {
   constexpr int R = IROW_RING, PD = IROW_PD, NS = IROW_NS;
+  constexpr unsigned SB = IROW_STAGE_BYTES;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int seg = lane / LR, ls = lane % LR;
   const int NW = gm.NW, ni = gm.ni, nj = gm.nj, nk = gm.nk, nkt = gm.nkt;
@@ -155,7 +156,7 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
   const int jstep = (jd > 0) ? ni : -ni;
   const int gstride = (int)gridDim.x;
 
-  const unsigned stage0 = sh.stage + (unsigned)(w * NS) * IROW_STAGE_BYTES + 16u * lane;  // + slot * IROW_STAGE_BYTES
+  const unsigned stage0 = sh.stage + (unsigned)(w * NS) * SB + 16u * lane;  // + slot * SB
   const unsigned kin0 = sh.kin + 16u * lane;                                               // + slot * 1024 (warp 0)
   const unsigned fk_in0 = sh.fkx + (unsigned)w * 1024u + 16u * lane;                       // + ring slot * (NW+1)*1024
   const unsigned fkx_slot = (unsigned)(NW + 1) * 1024u;
@@ -176,7 +177,7 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
   // Loads of row `r` (0-based in item `it`, r < nj) whose step is qn: rhs, sigt, the i-face flux and, for
   // warp 0, the tile-boundary k faces.  All by cp.async; each lane reads back only what it copied itself.
   auto prefetch = [&](const IItem &it, int r, bool ktile0, unsigned qn, unsigned sqn) {
-    const unsigned st = stage0 + sqn * IROW_STAGE_BYTES;
+    const unsigned st = stage0 + sqn * SB;
     const unsigned roff = (unsigned)(r * jstep);
     const double *rp = ds.rhs + (it.off0 + roff), *sp = ds.sigt + (it.soff0 + roff);
     ir_cp_async16(st, rp, 16); ir_cp_async16(st + 512, rp + 2, 16);
@@ -235,6 +236,7 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
     const int kl = t * NW + w;
     const bool k_out_global = (kl == nk - 1) || (w == NW - 1);
     const double cx = sh.cxt[it.d], cz = sh.tzc[it.d] * sh.rdz[it.kz], tyc = sh.tyc[it.d];
+    const double wd = POP ? wq[it.d] : 0.0;  // quadrature weight of this segment's direction
     unsigned off = it.off0, ipx = it.ipx0;
     int jz = (jd > 0) ? 0 : nj - 1;
 
@@ -250,8 +252,11 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
       ir_cp_async_commit();
       ir_cp_async_wait<PD>();  // the copies issued PD steps ago for this row have landed
 
+      double v4[4];  // zone volumes of this row (fused population): in flight while the row is computed
+      if (POP) ir_ldg256_nc(vol + (off - (unsigned)it.d * gm.sa - (unsigned)it.g * gm.sg), v4);
+
       // ---- everything that does not need the upwind k and j faces ----
-      const unsigned st = stage0 + sq * IROW_STAGE_BYTES;
+      const unsigned st = stage0 + sq * SB;
       double A[4], rc[4], r4[4];
       const double cy = tyc * sh.rdy[jz];
       {
@@ -345,9 +350,6 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
       if (it.ev) {
         ir_stg256(ds.psi + off, p4);
         if (POP) {
-          double v4[4];
-          ir_ldg256_nc(vol + ((unsigned)((it.kz * nj + jz) * ni) + i0), v4);
-          const double wd = wq[it.d];
 #pragma unroll
           for (int u = 0; u < 4; ++u) pop = fma(wd * p4[u], v4[u], pop);
         }
@@ -387,7 +389,8 @@ __global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sw
                                                              const double *const *__restrict__ pop_vol,
                                                              double *__restrict__ pop_partial) {
   extern __shared__ __align__(16) unsigned char ism[];
-  __shared__ kb200_sweep_desc ds;  // the descriptor is read all the time: keep it one LDS away
+  __shared__ kb200_sweep_desc ds;  // the descriptor is read all the time: keep it one LDS away (measured: faster than
+  // passing the descriptors by value and reading them through the constant bank)
   if (threadIdx.x < sizeof(kb200_sweep_desc) / sizeof(int))
     reinterpret_cast<int *>(&ds)[threadIdx.x] = reinterpret_cast<const int *>(&descs[blockIdx.y])[threadIdx.x];
   __syncthreads();

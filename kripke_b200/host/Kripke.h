@@ -336,6 +336,8 @@ class FieldStorageBase : public DomainVar {
   // define every element of the chunk on the device
   bool consumeZeroPending(SdomId sdom_id);
   bool isZeroPending(SdomId sdom_id) const { return m_chunks[m_subdomain_to_chunk[*sdom_id]].zero_pending; }
+  // bumped by every access that may change the chunk's contents (used to validate results cached from it)
+  unsigned long writeEpoch(SdomId sdom_id) const { return m_chunks[m_subdomain_to_chunk[*sdom_id]].write_epoch; }
   // device pointer for a kernel that defines the whole chunk (no upload, no memset)
   void *devPtrOverwrite(SdomId sdom_id);
   void releaseHostMirrors();
@@ -344,6 +346,7 @@ class FieldStorageBase : public DomainVar {
     void *dev = nullptr;
     void *host = nullptr;
     bool host_valid = false, dev_valid = false, zero_pending = false;
+    unsigned long write_epoch = 0;
   };
   void materializeZero(Chunk &c, size_t bytes);
   Set const *m_set;
@@ -544,7 +547,12 @@ void scattering(Core::DataStore &data_store);
 void source(Core::DataStore &data_store);
 void sweepSubdomain(Core::DataStore &data_store, SdomId sdom_id);
 // batched form: all subdomains of the list must be mutually independent (used by SweepSolver)
-void sweepSubdomains(Core::DataStore &data_store, std::vector<SdomId> const &sdom_ids, bool deliver_downwind);
+void sweepSubdomains(Core::DataStore &data_store, std::vector<SdomId> const &sdom_ids, bool deliver_downwind,
+                     bool fuse_population = false);
+// Population fused into the sweep: SweepSolver brackets its sweeps with begin/end; population()
+// returns the sum the sweep kernels accumulated if psi has not been touched since, else recomputes.
+void populationFusionBegin(Core::DataStore &data_store);
+void populationFusionEnd(Core::DataStore &data_store, std::vector<SdomId> const &swept);
 
 template <typename FieldType>
 void kConst(FieldType &field, SdomId sdom_id, typename FieldType::ElementType value) {

@@ -442,7 +442,7 @@ void *FieldStorageBase::hostPtr(SdomId sdom_id, bool will_write) {
     // else: never written anywhere -- uninitialised, exactly like the reference's new ELEMENT[] (Field.h:69)
     c.host_valid = true;
   }
-  if (will_write) c.dev_valid = false;
+  if (will_write) { c.dev_valid = false; ++c.write_epoch; }
   return c.host;
 }
 void *FieldStorageBase::devPtr(SdomId sdom_id, bool will_write) {
@@ -465,7 +465,7 @@ void *FieldStorageBase::devPtr(SdomId sdom_id, bool will_write) {
     }
     c.dev_valid = true;
   }
-  if (will_write) c.host_valid = false;
+  if (will_write) { c.host_valid = false; ++c.write_epoch; }
   return c.dev;
 }
 void *FieldStorageBase::devPtrOverwrite(SdomId sdom_id) {
@@ -475,6 +475,7 @@ void *FieldStorageBase::devPtrOverwrite(SdomId sdom_id) {
   c.dev_valid = true;
   c.host_valid = false;
   c.zero_pending = false;
+  ++c.write_epoch;
   return c.dev;
 }
 void FieldStorageBase::setZeroPending(SdomId sdom_id) {
@@ -482,6 +483,7 @@ void FieldStorageBase::setZeroPending(SdomId sdom_id) {
   c.zero_pending = true;
   c.host_valid = false;
   c.dev_valid = false;
+  ++c.write_epoch;
 }
 bool FieldStorageBase::consumeZeroPending(SdomId sdom_id) {
   Chunk &c = m_chunks[m_subdomain_to_chunk[*sdom_id]];

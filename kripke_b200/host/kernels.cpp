@@ -190,8 +190,69 @@ void Kripke::Kernel::source(DataStore &data_store) {
 }
 
 // ---- population: src/Kripke/Kernel/Population.cpp:74-101 ------------------------------------------------------------
+namespace {
+// State of the population sum accumulated by the sweep kernels (one per process: one DataStore is solved at a time).
+struct PopFusion {
+  double *d_partials = nullptr;  // device scratch the sweep launches of one SweepSolver pass append to
+  int capacity = 0, used = 0;
+  bool collecting = false, complete = false;
+  const void *psi = nullptr;               // the field the partials belong to
+  std::vector<unsigned long> epochs;       // write epoch of every psi chunk right after it was swept
+  std::vector<char> fused;                 // chunk was swept by a kernel that produced partials
+};
+PopFusion g_pop;
+bool popFusionEnabled() {
+  const char *e = getenv("KB200_FUSE_POP");
+  return !(e && e[0] == '0');
+}
+}  // namespace
+
+void Kripke::Kernel::populationFusionBegin(DataStore &data_store) {
+  g_pop.collecting = false;
+  g_pop.complete = false;
+  if (!popFusionEnabled()) return;
+  auto &field_psi = data_store.getVariable<Field_Flux>("psi");
+  if (!g_pop.d_partials) {
+    g_pop.capacity = 1 << 16;
+    KB200_CALL(kb200_alloc((size_t)g_pop.capacity * sizeof(double), (void **)&g_pop.d_partials));
+  }
+  const size_t n = data_store.getVariable<PartitionSpace>("pspace").getNumSubdomains(SPACE_PQR);
+  g_pop.used = 0;
+  g_pop.psi = &field_psi;
+  g_pop.epochs.assign(n, 0);
+  g_pop.fused.assign(n, 0);
+  g_pop.collecting = true;
+}
+
+void Kripke::Kernel::populationFusionEnd(DataStore &data_store, std::vector<SdomId> const &swept) {
+  if (!g_pop.collecting) return;
+  g_pop.collecting = false;
+  auto &field_psi = data_store.getVariable<Field_Flux>("psi");
+  // complete only if every chunk of psi was swept with partials in this pass, exactly once
+  size_t n_fused = 0;
+  for (char f : g_pop.fused) n_fused += f ? 1 : 0;
+  g_pop.complete = (&field_psi == g_pop.psi) && n_fused == g_pop.fused.size() && swept.size() == g_pop.fused.size();
+}
+
 double Kripke::Kernel::population(DataStore &data_store) {
   KRIPKE_TIMER(data_store, Population);
+  if (g_pop.complete && g_pop.psi == &data_store.getVariable<Field_Flux>("psi")) {
+    auto &psi = data_store.getVariable<Field_Flux>("psi");
+    bool valid = true;
+    for (SdomId s : psi.getWorkList())
+      if ((size_t)*s >= g_pop.epochs.size() || psi.writeEpoch(s) != g_pop.epochs[*s]) { valid = false; break; }
+    if (valid) {  // psi is exactly what the sweeps left: finish the sum they accumulated
+      static double *d_res = nullptr;
+      if (!d_res) KB200_CALL(kb200_alloc(sizeof(double), (void **)&d_res));
+      KB200_CALL(kb200_population_reduce(g_pop.d_partials, g_pop.used, d_res, nullptr));
+      KB200_CALL(kb200_comm_allreduce_sum_f64(d_res, 1, nullptr));
+      double part = 0.0;
+      KB200_CALL(kb200_download(&part, d_res, sizeof(double), nullptr));
+      KB200_CALL(kb200_stream_sync(nullptr));
+      return part;
+    }
+    g_pop.complete = false;
+  }
   Set const &set_dir = data_store.getVariable<Set>("Set/Direction");
   Set const &set_group = data_store.getVariable<Set>("Set/Group");
   Set const &set_zone = data_store.getVariable<Set>("Set/Zone");
@@ -226,7 +287,8 @@ double Kripke::Kernel::population(DataStore &data_store) {
 }
 
 // ---- sweepSubdomain(s): src/Kripke/Kernel/SweepSubdomain.cpp:115-124 ---------------------------------------------------
-void Kripke::Kernel::sweepSubdomains(DataStore &data_store, std::vector<SdomId> const &sdom_ids, bool deliver_downwind) {
+void Kripke::Kernel::sweepSubdomains(DataStore &data_store, std::vector<SdomId> const &sdom_ids, bool deliver_downwind,
+                                     bool fuse_population) {
   if (sdom_ids.empty()) return;
   KRIPKE_TIMER(data_store, SweepSubdomain);
   auto &pspace = data_store.getVariable<PartitionSpace>("pspace");
@@ -287,6 +349,26 @@ void Kripke::Kernel::sweepSubdomains(DataStore &data_store, std::vector<SdomId> 
       }
     }
     descs.push_back(d);
+  }
+  if (fuse_population && g_pop.collecting && g_pop.psi == &f_psi) {
+    auto &f_w = data_store.getVariable<Field_Direction2Double>("quadrature/w");
+    auto &f_vol = data_store.getVariable<Field_Zone2Double>("volume");
+    std::vector<const double *> pw, pv;
+    for (SdomId s : sdom_ids) { pw.push_back(f_w.devicePtrConst(s)); pv.push_back(f_vol.devicePtrConst(s)); }
+    int count = 0;
+    KB200_CALL(kb200_sweep_population(descs.data(), (int)descs.size(), pw.data(), pv.data(), g_pop.d_partials + g_pop.used,
+                                      g_pop.capacity - g_pop.used, &count, nullptr));
+    if (count > 0) {
+      g_pop.used += count;
+      for (SdomId s : sdom_ids) {
+        g_pop.fused[*s] = g_pop.fused[*s] ? 2 : 1;  // 2 = swept twice: the partials would double count
+        g_pop.epochs[*s] = f_psi.writeEpoch(s);
+      }
+      for (char &f : g_pop.fused) if (f == 2) { g_pop.collecting = false; }
+    } else {
+      g_pop.collecting = false;  // some subdomains went through a kernel without the fused sum
+    }
+    return;
   }
   KB200_CALL(kb200_sweep(descs.data(), (int)descs.size(), nullptr));
 }

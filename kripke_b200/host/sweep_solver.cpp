@@ -302,6 +302,7 @@ void Kripke::SweepSolver(DataStore &data_store, std::vector<SdomId> subdomain_li
   auto &field_upwind = data_store.getVariable<Field_Adjacency>("upwind");
   const bool deliver = !block_jacobi;  // the kernel writes outgoing faces straight into on-rank downwind chunks
   comm->setDelivered(deliver);
+  Kernel::populationFusionBegin(data_store);
 
   while (comm->workRemaining()) {
     std::vector<SdomId> ready = comm->readySubdomains();
@@ -312,8 +313,9 @@ void Kripke::SweepSolver(DataStore &data_store, std::vector<SdomId> subdomain_li
       if (upwind[1] == -1) Kernel::kConst(j_plane, sdom_id, 0.0);
       if (upwind[2] == -1) Kernel::kConst(k_plane, sdom_id, 0.0);
     }
-    Kernel::sweepSubdomains(data_store, ready, deliver);
+    Kernel::sweepSubdomains(data_store, ready, deliver, true);
     for (SdomId sdom_id : ready) comm->markComplete(sdom_id);
   }
+  Kernel::populationFusionEnd(data_store, subdomain_list);
   delete comm;
 }
