@@ -39,8 +39,9 @@ constexpr int IROW_RING = 2;   // slots of the k-face ring between neighbouring 
 constexpr int IROW_PD = 2;     // prefetch distance in row steps
 constexpr int IROW_NS = IROW_PD + 1;  // staging slots per warp
 constexpr int IROW_MAXW = 16, IROW_MAXT = IROW_MAXW * 32;  // warps per CTA: up to 128 registers per thread
-// per warp and staging slot: rhs [2][32] double2, sigt [2][32] double2, incoming i face [32] double
-constexpr int IROW_STAGE_BYTES = 1024 + 1024 + 256;
+// per warp and staging slot: the rhs rows and the sigt rows of the warp's ER elements in memory order (1 KB each)
+// (+ one row of zone volumes, shared by the ER segments, when the population sum is fused in)
+constexpr int IROW_STAGE_BYTES = 1024 + 1024, IROW_STAGE_BYTES_POP = IROW_STAGE_BYTES + 1024;
 
 struct IGeom {  // kernel parameter: lives in the constant bank, costs no registers
   int layout, Ds, Gs, ni, nj, nk;
@@ -92,6 +93,19 @@ __device__ __forceinline__ void ir_wait_ge(unsigned addr, unsigned target) {
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   } while ((int)(v - target) < 0);
 }
+// TMA bulk copy global -> shared (contiguous bytes, 16-byte aligned, multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void ir_bulk_g2s(unsigned smem_dst, const void *gsrc, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void ir_mb_expect_tx(unsigned addr, unsigned bytes) {
+  asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ double ir_ld_cg(const double *p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void ir_mb_init(unsigned addr, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
 }
@@ -107,6 +121,7 @@ struct IShared {  // shared-window addresses of the pieces of dynamic shared mem
   unsigned kin;          // [IROW_NS][2][32] double2: warp 0's tile-boundary k faces
   unsigned stage;        // [NW][IROW_NS] staging slots of IROW_STAGE_BYTES
   unsigned full, empty;  // [NW+1][IROW_RING] mbarriers of the ring slots (32 arrivals each)
+  unsigned sbar;         // [NW][IROW_NS] mbarriers of the staging slots (1 arrival + the bytes of the bulk copies)
   unsigned prod;         // [1] rows whose tile-boundary k faces the last warp has put into k_plane
   const double *cxt, *txc, *tyc, *tzc, *rdy, *rdz;  // [Ds] 2*xcos/dx[0], 2*xcos, 2*ycos, 2*zcos ; [nj] 1/dy ; [nk] 1/dz
 };
@@ -116,8 +131,8 @@ struct IItem {
   int d, g;                    // phase-space element of this lane's segment
   bool ev, kv;                 // segment holds a real element; this warp's k-plane exists in the tile
   int kz;                      // memory k index of the plane
-  unsigned off0, soff0, ipx0;  // element offsets of the item's first row: rhs/psi block, sigt block, i_plane entry
-  unsigned kpx0;               // k_plane block of the first row (warp 0 only)
+  unsigned off0, soff0, ipx0;  // element offsets of the item's first row (its i = 0 zone): rhs/psi, sigt, i_plane entry
+  unsigned kpx0;               // k_plane row of the first row (warp 0 only)
 };
 
 template <int LR>
@@ -134,11 +149,12 @@ __device__ __forceinline__ IItem irow_item(const IGeom &gm, int gi, int t, int w
   const int klc = it.kv ? kl : gm.nk - 1;
   it.kz = (kd > 0) ? klc : gm.nk - 1 - klc;
   const int jz0 = (jd > 0) ? 0 : gm.nj - 1;
-  const unsigned zoff = (unsigned)((it.kz * gm.nj + jz0) * gm.ni) + i0;
+  const unsigned zoff = (unsigned)((it.kz * gm.nj + jz0) * gm.ni);
+  (void)i0;
   it.off0 = (unsigned)it.d * gm.sa + (unsigned)it.g * gm.sg + zoff;
   it.soff0 = (unsigned)it.g * gm.Zs + zoff;
   it.ipx0 = (unsigned)it.d * gm.ipd + (unsigned)it.g * gm.ipg + (unsigned)(it.kz * gm.nj + jz0);
-  it.kpx0 = (unsigned)it.d * gm.kpd + (unsigned)it.g * gm.kpg + (unsigned)(jz0 * gm.ni) + i0;
+  it.kpx0 = (unsigned)it.d * gm.kpd + (unsigned)it.g * gm.kpg + (unsigned)(jz0 * gm.ni);
   return it;
 }
 
@@ -146,7 +162,7 @@ template <int LR, bool FWD, bool UNI, bool POP>
 __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGeom &gm, const IShared &sh,
                                            const double *__restrict__ wq, const double *__restrict__ vol) {
   constexpr int R = IROW_RING, PD = IROW_PD, NS = IROW_NS;
-  constexpr unsigned SB = IROW_STAGE_BYTES;
+  constexpr unsigned SB = POP ? IROW_STAGE_BYTES_POP : IROW_STAGE_BYTES;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int seg = lane / LR, ls = lane % LR;
   const int NW = gm.NW, ni = gm.ni, nj = gm.nj, nk = gm.nk, nkt = gm.nkt;
@@ -156,8 +172,11 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
   const int jstep = (jd > 0) ? ni : -ni;
   const int gstride = (int)gridDim.x;
 
-  const unsigned stage0 = sh.stage + (unsigned)(w * NS) * SB + 16u * lane;  // + slot * SB
-  const unsigned kin0 = sh.kin + 16u * lane;                                               // + slot * 1024 (warp 0)
+  const unsigned rowb = 8u * (unsigned)ni;                                  // bytes of one i-row
+  const unsigned stage0 = sh.stage + (unsigned)(w * NS) * SB;               // + slot * SB : [rhs rows of the ER segments][sigt rows]
+  const unsigned kin0 = sh.kin;                                             // + slot * 1024 (warp 0): k_plane rows of the ER segments
+  const unsigned sbar0 = sh.sbar + 8u * (unsigned)(w * NS);                 // + 8 * slot
+  const unsigned mine = (unsigned)seg * rowb + 8u * i0;                     // this lane's four zones inside a staged row block
   const unsigned fk_in0 = sh.fkx + (unsigned)w * 1024u + 16u * lane;                       // + ring slot * (NW+1)*1024
   const unsigned fkx_slot = (unsigned)(NW + 1) * 1024u;
   const unsigned full_in = sh.full + 8u * (unsigned)(w * R), full_out = full_in + 8u * R;
@@ -172,35 +191,36 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
   unsigned q = 0;     // row steps done by this warp
   unsigned slot = 0;  // q % R
   unsigned ph = 0;    // (q / R) & 1: phase parity of the ring slot's current use
-  unsigned sq = 0;    // q % NS: staging slot of the current row
+  unsigned sq = 0;    // staging slot of the current row (advances with the rows this warp actually computes)
+  unsigned sph = 0;   // phase parity of that slot's current use
+  double fi0n = 0.0;  // incoming i-face flux of the next row
 
-  // Loads of row `r` (0-based in item `it`, r < nj) whose step is qn: rhs, sigt, the i-face flux and, for
-  // warp 0, the tile-boundary k faces.  All by cp.async; each lane reads back only what it copied itself.
+  // Loads of row `r` (0-based in item `it`, r < nj) whose step is qn, into staging slot sqn: one TMA bulk copy per
+  // element row for rhs, sigt and (warp 0) the tile-boundary k faces, completion counted on the slot's mbarrier.
   auto prefetch = [&](const IItem &it, int r, bool ktile0, unsigned qn, unsigned sqn) {
-    const unsigned st = stage0 + sqn * SB;
-    const unsigned roff = (unsigned)(r * jstep);
-    const double *rp = ds.rhs + (it.off0 + roff), *sp = ds.sigt + (it.soff0 + roff);
-    ir_cp_async16(st, rp, 16); ir_cp_async16(st + 512, rp + 2, 16);
-    ir_cp_async16(st + 1024, sp, 16); ir_cp_async16(st + 1536, sp + 2, 16);
-    ir_cp_async8(st + 2048 - 8u * lane, ds.i_plane + (it.ipx0 + (unsigned)(r * jd)), i_zero ? 0 : 8);
-    if (w == 0) {
-      // rows of a later k tile were written by the tile's predecessor nj row steps earlier
-      if (!ktile0) ir_wait_ge(sh.prod, qn + 1u - (unsigned)nj);
-      const double *src = ds.k_plane + (it.kpx0 + roff);
-      const int sz = (k_zero && ktile0) ? 0 : 16;  // vacuum: zero fill
-      const unsigned dst = kin0 + sqn * 1024u;
-      ir_cp_async16(dst, src, sz);
-      ir_cp_async16(dst + 512, src + 2, sz);
+    const bool kload = (w == 0) && !(k_zero && ktile0);
+    // rows of a later k tile were written by the tile's predecessor nj row steps earlier
+    if (w == 0 && !ktile0) ir_wait_ge(sh.prod, qn + 1u - (unsigned)nj);
+    const unsigned bar = sbar0 + 8u * sqn;
+    if (lane == 0) ir_mb_expect_tx(bar, (kload ? 3u : 2u) * rowb * (unsigned)(32 / LR) + (POP ? rowb : 0u));
+    __syncwarp();  // also: every lane is done reading the slot's previous contents
+    if (ls == 0) {
+      const unsigned roff = (unsigned)(r * jstep);
+      const unsigned dst = stage0 + sqn * SB + (unsigned)seg * rowb;
+      ir_bulk_g2s(dst, ds.rhs + (it.off0 + roff), rowb, bar);
+      ir_bulk_g2s(dst + 1024, ds.sigt + (it.soff0 + roff), rowb, bar);
+      if (kload) ir_bulk_g2s(kin0 + sqn * 1024u + (unsigned)seg * rowb, ds.k_plane + (it.kpx0 + roff), rowb, bar);
+      if (POP && lane == 0)  // the zone volumes of the row: the same for every element
+        ir_bulk_g2s(stage0 + sqn * SB + 2048, vol + (it.soff0 - (unsigned)it.g * gm.Zs + roff), rowb, bar);
     }
   };
   auto next_sq = [](unsigned s, int by) { unsigned v = s + (unsigned)by; return v >= (unsigned)NS ? v - NS : v; };
 
-  // prologue: rows 0..PD-1 of the first item, one cp.async group per row
+  // prologue: rows 0..PD-1 of the first item
 #pragma unroll
-  for (int r = 0; r < PD; ++r) {
+  for (int r = 0; r < PD; ++r)
     if (nx_ok && nx.kv && r < nj) prefetch(nx, r, true, (unsigned)r, (unsigned)r);
-    ir_cp_async_commit();
-  }
+  if (nx_ok && nx.kv && !i_zero) fi0n = ir_ld_cg(ds.i_plane + nx.ipx0);
 
   while (nx_ok) {
     const IItem it = nx;
@@ -220,15 +240,12 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
           ir_mb_arrive(full_out + 8u * slot);
         }
         ++q;
-        sq = next_sq(sq, 1);
         if (++slot == R) { slot = 0; ph ^= 1u; }
       }
-      ir_cp_async_wait<0>();
 #pragma unroll
-      for (int r = 0; r < PD; ++r) {  // the next item (tile 0 of the next group) starts from scratch
+      for (int r = 0; r < PD; ++r)  // the next item (tile 0 of the next group) starts from scratch
         if (nx_pre && r < nj) prefetch(nx, r, nt == 0, q + (unsigned)r, next_sq(sq, r));
-        ir_cp_async_commit();
-      }
+      if (nx_pre && !i_zero) fi0n = ir_ld_cg(ds.i_plane + nx.ipx0);
       gi = ngi; t = nt;
       continue;
     }
@@ -249,20 +266,21 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
         if (r < nj) prefetch(it, r, ktile0, q + (unsigned)PD, sqn);
         else if (nx_pre && r - nj < nj) prefetch(nx, r - nj, nt == 0, q + (unsigned)PD, sqn);
       }
-      ir_cp_async_commit();
-      ir_cp_async_wait<PD>();  // the copies issued PD steps ago for this row have landed
-
-      double v4[4];  // zone volumes of this row (fused population): in flight while the row is computed
-      if (POP) ir_ldg256_nc(vol + (off - (unsigned)it.d * gm.sa - (unsigned)it.g * gm.sg), v4);
+      const double fi0 = fi0n;
+      if (!i_zero) {  // incoming i-face flux of the next row: one step ahead, in a register
+        if (j + 1 < nj) fi0n = ir_ld_cg(ds.i_plane + (ipx + (unsigned)jd));
+        else if (nx_pre) fi0n = ir_ld_cg(ds.i_plane + nx.ipx0);
+      }
+      ir_mb_wait(sbar0 + 8u * sq, sph);  // the bulk copies issued PD steps ago for this row have landed
 
       // ---- everything that does not need the upwind k and j faces ----
-      const unsigned st = stage0 + sq * SB;
+      const unsigned st = stage0 + sq * SB + mine;
       double A[4], rc[4], r4[4];
       const double cy = tyc * sh.rdy[jz];
       {
-        const double2 e = ir_lds128(st + 1024), f = ir_lds128(st + 1536);
+        const double2 e = ir_lds128(st + 1024), f = ir_lds128(st + 1024 + 16);
         const double s4[4] = {e.x, e.y, f.x, f.y};
-        const double2 a = ir_lds128(st), b = ir_lds128(st + 512);
+        const double2 a = ir_lds128(st), b = ir_lds128(st + 16);
         r4[0] = a.x; r4[1] = a.y; r4[2] = b.x; r4[3] = b.y;
         const double csum = __dadd_rn(__dadd_rn(cx, cy), cz);
 #pragma unroll
@@ -282,7 +300,6 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
           A[u] = cxu * rc[u];
         }
       }
-      const double fi0 = ir_lds64(st + 2048 - 8u * lane);
       if (j == 0) {
         if (j_zero) { fj[0] = fj[1] = fj[2] = fj[3] = 0.0; }
         else ir_ldg256_cg(ds.j_plane + ((unsigned)it.d * gm.jpd + (unsigned)it.g * gm.jpg + (unsigned)(it.kz * ni) + i0), fj);
@@ -293,12 +310,19 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
       // ---- upwind k faces: from warp w-1 through the ring, or (warp 0) from the staged k_plane row ----
       double fk[4];
       {
-        unsigned src = fk_in0 + slot * fkx_slot;
-        if (w > 0) ir_mb_wait(full_in + 8u * slot, ph);
-        else src = kin0 + sq * 1024u;
-        const double2 k0 = ir_lds128(src), k1 = ir_lds128(src + 512);
-        fk[0] = k0.x; fk[1] = k0.y; fk[2] = k1.x; fk[3] = k1.y;
-        if (w > 0) ir_mb_arrive(empty_in + 8u * slot);  // the slot may be refilled
+        if (w > 0) {
+          ir_mb_wait(full_in + 8u * slot, ph);
+          const unsigned src = fk_in0 + slot * fkx_slot;
+          const double2 k0 = ir_lds128(src), k1 = ir_lds128(src + 512);
+          fk[0] = k0.x; fk[1] = k0.y; fk[2] = k1.x; fk[3] = k1.y;
+          ir_mb_arrive(empty_in + 8u * slot);  // the slot may be refilled
+        } else if (k_zero && ktile0) {
+          fk[0] = fk[1] = fk[2] = fk[3] = 0.0;
+        } else {
+          const unsigned src = kin0 + sq * 1024u + mine;
+          const double2 k0 = ir_lds128(src), k1 = ir_lds128(src + 16);
+          fk[0] = k0.x; fk[1] = k0.y; fk[2] = k1.x; fk[3] = k1.y;
+        }
       }
       // B = (rhs + fj*cy + fk*cz) / den ; this lane's composite map  fi_out = al * fi_in + be
       double B[4];
@@ -348,8 +372,11 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
         ir_mb_arrive(full_out + 8u * slot);
       }
       if (it.ev) {
-        ir_stg256(ds.psi + off, p4);
+        ir_stg256(ds.psi + (off + i0), p4);
         if (POP) {
+          const unsigned vs = stage0 + sq * SB + 2048 + 8u * i0;
+          const double2 va = ir_lds128(vs), vb = ir_lds128(vs + 16);
+          const double v4[4] = {va.x, va.y, vb.x, vb.y};
 #pragma unroll
           for (int u = 0; u < 4; ++u) pop = fma(wd * p4[u], v4[u], pop);
         }
@@ -363,7 +390,7 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
           if (ds.out_plane[1]) ir_stg256(ds.out_plane[1] + jpx, fj);
         }
         if (k_out_global) {
-          const unsigned kpx = it.kpx0 + (unsigned)(j * jstep);
+          const unsigned kpx = it.kpx0 + (unsigned)(j * jstep) + i0;
           ir_stg256(ds.k_plane + kpx, ok);
           if (kl == nk - 1 && ds.out_plane[2]) ir_stg256(ds.out_plane[2] + kpx, ok);
         }
@@ -373,13 +400,12 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
         if (lane == 0) ir_st_release(sh.prod, q + 1u);
       }
       ++q;
-      sq = next_sq(sq, 1);
+      if (++sq == (unsigned)NS) { sq = 0; sph ^= 1u; }
       if (++slot == R) { slot = 0; ph ^= 1u; }
       off += (unsigned)jstep; ipx += (unsigned)jd; jz += jd;
     }
     gi = ngi; t = nt;
   }
-  ir_cp_async_wait<0>();
   return pop;
 }
 
@@ -399,18 +425,21 @@ __global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sw
   unsigned char *p = ism;
   sh.fkx = ir_smem_addr(p); p += (size_t)IROW_RING * (NW + 1) * 1024;
   sh.kin = ir_smem_addr(p); p += (size_t)IROW_NS * 1024;
-  sh.stage = ir_smem_addr(p); p += (size_t)NW * IROW_NS * IROW_STAGE_BYTES;
+  sh.stage = ir_smem_addr(p); p += (size_t)NW * IROW_NS * (POP ? IROW_STAGE_BYTES_POP : IROW_STAGE_BYTES);
   double *tab = reinterpret_cast<double *>(p);
   double *cxt = tab, *txc = cxt + Ds, *tyc = txc + Ds, *tzc = tyc + Ds, *rdy = tzc + Ds, *rdz = rdy + nj;
   double *red = rdz + nk;  // [32] block reduction of the population partials
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(red + 32);
   sh.full = ir_smem_addr(bars);
   sh.empty = sh.full + 8u * (unsigned)((NW + 1) * IROW_RING);
-  unsigned *prod = reinterpret_cast<unsigned *>(bars + 2 * (NW + 1) * IROW_RING);
+  sh.sbar = sh.empty + 8u * (unsigned)((NW + 1) * IROW_RING);
+  unsigned *prod = reinterpret_cast<unsigned *>(bars + 2 * (NW + 1) * IROW_RING + NW * IROW_NS);
   sh.prod = ir_smem_addr(prod);
   sh.cxt = cxt; sh.txc = txc; sh.tyc = tyc; sh.tzc = tzc; sh.rdy = rdy; sh.rdz = rdz;
   if (threadIdx.x == 0) *prod = 0u;
   if ((int)threadIdx.x < 2 * (NW + 1) * IROW_RING) ir_mb_init(sh.full + 8u * threadIdx.x, 32u);
+  if ((int)threadIdx.x < NW * IROW_NS) ir_mb_init(sh.sbar + 8u * threadIdx.x, 1u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // the TMA unit sees initialised barriers
 
   // 2*cos tables and reciprocal zone widths (SweepSubdomain.cpp:88-93), indexed by the MEMORY zone index
   for (int d = threadIdx.x; d < Ds; d += blockDim.x) {
@@ -508,8 +537,8 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
   // rows are fetched IROW_PD steps ahead, at most into the next item; warp 0 must not wait for tile-boundary
   // k faces of a row the last warp can only produce after warp 0 has moved on
   if (nj <= IROW_PD) return -1;
-  const size_t smem = (size_t)IROW_RING * (gm.NW + 1) * 1024 + (size_t)IROW_NS * 1024 + (size_t)gm.NW * IROW_NS * IROW_STAGE_BYTES +
-                      ((size_t)4 * gm.Ds + nj + nk + 32 + 2 * (gm.NW + 1) * IROW_RING + 2) * sizeof(double);
+  const size_t smem = (size_t)IROW_RING * (gm.NW + 1) * 1024 + (size_t)IROW_NS * 1024 + (size_t)gm.NW * IROW_NS * IROW_STAGE_BYTES_POP +
+                      ((size_t)4 * gm.Ds + nj + nk + 32 + 2 * (gm.NW + 1) * IROW_RING + gm.NW * IROW_NS + 2) * sizeof(double);
   if (smem > 226 * 1024) return -1;
   const int ER = 32 / LR;
   const int ngroups = (gm.Ds * gm.Gs + ER - 1) / ER;
