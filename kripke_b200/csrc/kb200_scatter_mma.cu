@@ -20,7 +20,7 @@
 namespace kb200 {
 
 struct ScatGeom {
-  int layout, M, L1, G, Gs, Zs, nsrc, accumulate;
+  int layout, sigs_layout, M, L1, G, Gs, Zs, nsrc, accumulate;  // sigs may keep another nesting's order (transform path)
   int O, K, nkc4;          // outputs of one o-chunk launch slice (<= 32 per CTA), reduction length, k-chunks
   int KC, nst;             // slab rows, slabs per tile
   long long in_b, in_r;    // moment (batch) stride, group (row) stride of phi / phi_out
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scatter
     inrow[k] = p;
   }
   __syncthreads();
-  const Strides4 ss = strides_sigs(gm.layout, gm.L1, gm.G);
+  const Strides4 ss = strides_sigs(gm.sigs_layout, gm.L1, gm.G);
 
   const long long ntiles = (long long)gm.M * ntn;          // tile = (moment, zone tile), moment-major
   const int my_tiles = ((long long)blockIdx.x < ntiles) ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scatter
 using namespace kb200;
 
 // Returns 0 if handled, -1 if this path does not apply (caller falls back to the DFMA kernel), >0 on error.
-int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_descs, cudaStream_t st) {
+int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_descs, int sigs_layout, cudaStream_t st) {
   const int layout = h[0].layout;
   if (layout != 0 && layout != 2) return -1;
   const char *env = getenv("KB200_SCATTER_DFMA");
@@ -231,7 +231,7 @@ int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_d
   }
   ScatGeom gm;
   memset(&gm, 0, sizeof(gm));
-  gm.layout = layout; gm.M = h[0].M; gm.L1 = h[0].L1; gm.G = h[0].G; gm.Gs = h[0].Gs; gm.Zs = h[0].Zs;
+  gm.layout = layout; gm.sigs_layout = sigs_layout >= 0 ? sigs_layout : layout; gm.M = h[0].M; gm.L1 = h[0].L1; gm.G = h[0].G; gm.Gs = h[0].Gs; gm.Zs = h[0].Zs;
   gm.nsrc = h[0].nsrc; gm.accumulate = h[0].accumulate;
   gm.O = gm.Gs; gm.K = gm.nsrc * gm.Gs; gm.nkc4 = (gm.K + 3) / 4;
   const int Kp = gm.nkc4 * 4;

@@ -242,7 +242,8 @@ __global__ void layout_transform_kernel(int src_layout, int dst_layout, int na, 
 
 using namespace kb200;
 
-int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_descs, cudaStream_t st);  // kb200_scatter_mma.cu
+int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_descs, int sigs_layout, cudaStream_t st);  // kb200_scatter_mma.cu
+int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, cudaStream_t st);  // kb200_scatter_row.cu
 
 extern "C" {
 
@@ -263,7 +264,9 @@ int kb200_scattering(const kb200_scattering_desc *h, int n, kb200_stream_t strea
   int rc = device_descs(h, sizeof(*h) * n, &d, st);
   if (rc) return rc;
   if (!exact_mode()) {  // default arithmetic: fp64 tensor-core path for the zone-fastest layouts
-    rc = kb200_scatter_mma_try(h, n, d, st);
+    rc = kb200_scatter_mma_try(h, n, d, -1, st);
+    if (rc >= 0) return rc;
+    rc = kb200_scatter_row_try(h, n, st);  // moment-fastest layouts: transposed through the zone-fastest kernel
     if (rc >= 0) return rc;
   }
   constexpr int GT = 8;

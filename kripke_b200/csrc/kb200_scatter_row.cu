@@ -1,0 +1,133 @@
+// Scattering for the moment-fastest storage orders (GZD, ZGD), default arithmetic.
+//
+// In these nestings phi[.][.][nm] has the moment index fastest, so the group-to-group contraction
+// (Kernel/Scattering.cpp:73-99) would have to gather its operand with a 200-byte stride.  The moments
+// field is small (16*N_m bytes against 40*N_u for the whole iteration), so the cheapest correct
+// design is the layout-transform boundary of SURVEY 8b2: each source chunk is transposed once into
+// the zone-fastest order [nm][g][z] (tiled through shared memory, both sides coalesced), the
+// tensor-core kernel of kb200_scatter_mma.cu runs on the transposed chunks (sigs stays in its own
+// nesting's order), and phi_out is transposed back -- with the caller's "+=" folded into that
+// last pass.  Extra traffic: 32*N_m bytes, about 2 x 1.1 ms at BASELINE config 2, instead of the
+// 30-50 ms of the strided DFMA kernel.  EXACT mode keeps the bit-ordered DFMA kernel.
+#include "kb200_common.cuh"
+#include <map>
+#include <vector>
+
+namespace kb200 {
+
+// one (group, 64-zone) tile: rows[z][nm] (moment-fastest side) <-> cols[nm][z] (zone-fastest side)
+constexpr int TRZ = 64;
+
+template <bool TO_ZONE_FASTEST>
+__global__ void __launch_bounds__(256) moments_transpose_kernel(const double *__restrict__ src, double *__restrict__ dst, int M, int Gs,
+                                                                int Zs, long long mf_sg, long long mf_sz, int accumulate) {
+  extern __shared__ double tsm[];  // [TRZ][MP]
+  const int MP = M | 1;            // odd row stride: conflict-free transposed access
+  const int g = blockIdx.y;
+  const int z0 = blockIdx.x * TRZ;
+  const int nz = min(TRZ, Zs - z0);
+  const long long zf_base = (long long)g * Zs + z0;          // + nm * Gs * Zs + zl   (zone-fastest side, DGZ order)
+  const long long mf_base = (long long)g * mf_sg + (long long)z0 * mf_sz;  // + zl * mf_sz + nm (moment-fastest side)
+  const long long zf_sa = (long long)Gs * Zs;
+  if (TO_ZONE_FASTEST) {
+    for (int f = threadIdx.x; f < nz * M; f += blockDim.x) {
+      const int zl = f / M, nm = f - zl * M;
+      tsm[zl * MP + nm] = __ldg(src + mf_base + (long long)zl * mf_sz + nm);
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < M * TRZ; f += blockDim.x) {
+      const int nm = f / TRZ, zl = f - nm * TRZ;
+      if (zl < nz) dst[zf_base + (long long)nm * zf_sa + zl] = tsm[zl * MP + nm];
+    }
+  } else {
+    for (int f = threadIdx.x; f < M * TRZ; f += blockDim.x) {
+      const int nm = f / TRZ, zl = f - nm * TRZ;
+      if (zl < nz) tsm[zl * MP + nm] = __ldg(src + zf_base + (long long)nm * zf_sa + zl);
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < nz * M; f += blockDim.x) {
+      const int zl = f / M, nm = f - zl * M;
+      double *q = dst + mf_base + (long long)zl * mf_sz + nm;
+      double v = tsm[zl * MP + nm];
+      if (accumulate) v += *q;
+      *q = v;
+    }
+  }
+}
+
+// scratch chunks in the zone-fastest order, kept between calls (freed when the process ends)
+struct RowScratch {
+  std::vector<double *> bufs;
+  size_t bytes_each = 0;
+};
+static RowScratch g_row_scratch;
+
+static int row_scratch(size_t count, size_t bytes_each, std::vector<double *> &out) {
+  RowScratch &rs = g_row_scratch;
+  if (rs.bytes_each < bytes_each) {
+    if (!rs.bufs.empty()) KB_CUDA(cudaDeviceSynchronize());
+    for (double *p : rs.bufs) cudaFree(p);
+    rs.bufs.clear();
+    rs.bytes_each = bytes_each;
+  }
+  while (rs.bufs.size() < count) {
+    double *p = nullptr;
+    KB_CUDA(cudaMalloc(&p, rs.bytes_each));
+    rs.bufs.push_back(p);
+  }
+  out.assign(rs.bufs.begin(), rs.bufs.begin() + count);
+  return 0;
+}
+
+}  // namespace kb200
+
+using namespace kb200;
+
+int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_descs, int sigs_layout, cudaStream_t st);  // kb200_scatter_mma.cu
+
+// Returns 0 if handled, -1 if this path does not apply (caller falls back to the DFMA kernel), >0 on error.
+int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, cudaStream_t st) {
+  const int layout = h[0].layout;
+  if (layout != 3 && layout != 5) return -1;
+  const char *env = getenv("KB200_SCATTER_DFMA");
+  if (env && env[0] == '1') return -1;
+  const int M = h[0].M, Gs = h[0].Gs, Zs = h[0].Zs;
+  if (Zs % 2 != 0) return -1;
+  const size_t chunk_bytes = (size_t)M * Gs * Zs * sizeof(double);
+  // distinct source chunks of the batch (the destination group sets of one zone set share them)
+  std::map<const double *, int> src_index;
+  for (int i = 0; i < n; ++i)
+    for (int s = 0; s < h[i].nsrc; ++s)
+      if (!src_index.count(h[i].phi_src[s])) { const int id = (int)src_index.size(); src_index[h[i].phi_src[s]] = id; }
+  const int nsrc = (int)src_index.size();
+  std::vector<double *> bufs;
+  int rc = row_scratch((size_t)nsrc + n, chunk_bytes, bufs);
+  if (rc) return rc;
+  const Strides3 ms = strides_dgz(layout, M, Gs, Zs);  // the moment-fastest side: ms.a == 1
+  const size_t smem = (size_t)TRZ * (M | 1) * sizeof(double);
+  if (smem > 48 * 1024) return -1;
+  const dim3 grid((Zs + TRZ - 1) / TRZ, Gs, 1);
+  for (auto &kv : src_index) {
+    moments_transpose_kernel<true><<<grid, 256, smem, st>>>(kv.first, bufs[kv.second], M, Gs, Zs, ms.g, ms.z, 0);
+    rc = post_launch("moments_transpose");
+    if (rc) return rc;
+  }
+  std::vector<kb200_scattering_desc> t(h, h + n);
+  for (int i = 0; i < n; ++i) {
+    t[i].layout = 0;
+    t[i].accumulate = 0;
+    for (int s = 0; s < t[i].nsrc; ++s) t[i].phi_src[s] = bufs[src_index[h[i].phi_src[s]]];
+    t[i].phi_out = bufs[nsrc + i];
+  }
+  const void *d = nullptr;
+  rc = device_descs(t.data(), sizeof(kb200_scattering_desc) * n, &d, st);
+  if (rc) return rc;
+  rc = kb200_scatter_mma_try(t.data(), n, d, layout, st);
+  if (rc != 0) return rc < 0 ? -1 : rc;
+  for (int i = 0; i < n; ++i) {
+    moments_transpose_kernel<false><<<grid, 256, smem, st>>>(bufs[nsrc + i], h[i].phi_out, M, Gs, Zs, ms.g, ms.z, h[i].accumulate);
+    rc = post_launch("moments_transpose");
+    if (rc) return rc;
+  }
+  return 0;
+}
