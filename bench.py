@@ -88,6 +88,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(workload, layout, kernel):
+    """DRAM bytes (read + write) per launch of the entry point's kernel, from the committed ncu --set full capture
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py); None if that capture does not exist."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)[f"{workload}:{layout}"]["per_entry_point"][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def run_reference_cpu(workload, layout, steps, warmup, zones):
     """times the unmodified reference (oracle/_ref/kripke_ref, OpenMP, all host threads) on a bounded
     sample of the workload: same groups/directions/legendre/layout, fewer zones."""
@@ -307,7 +318,9 @@ def main():
                 "gpu_launches": int(launches.value),
                 "clocks": clocks,
                 "roofline": {"kernel": dom, "bound": "hbm", "achieved": per_kernel[dom]["alg_GBs_per_gpu"], "peak": peak,
-                             "unit": "GB/s", "frac": per_kernel[dom]["frac_of_hbm_peak"], "traffic": None,
+                             "unit": "GB/s", "frac": per_kernel[dom]["frac_of_hbm_peak"],
+                             "traffic": ncu_traffic(args.workload, args.layout, dom) if n_gpus == 1 else None,
+                             "algorithmic_bytes": alg[dom] / n_gpus,
                              "peak_source": peak_src},
                 "per_kernel": per_kernel,
                 "particles_last": particles[-1] if particles else None,
