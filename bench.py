@@ -31,6 +31,7 @@ WORKLOADS = {
     "config2": ((64, 64, 64), 64, 192, 4, ""),                 # BASELINE configs[1] (headline)
     "config1": ((16, 16, 16), 32, 96, 4, ""),                  # configs[0], the reference's default
     "config3": ((32, 32, 32), 128, 128, 9, ""),                # configs[2], high scattering order
+    "config4": ((64, 64, 64), 64, 96, 4, "--zset 4,4,4 --gset 4 --dset 8"),  # configs[3], per-GPU share of the 8-GPU KBA sweep (16^3 subdomains)
     "config5": ((64, 64, 64), 32, 96, 4, "--pmethod bj"),      # configs[4], block Jacobi weak scaling
     "small": ((32, 32, 32), 32, 96, 4, ""),
 }

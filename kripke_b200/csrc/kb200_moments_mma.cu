@@ -53,6 +53,25 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// TMA bulk copy + mbarrier plumbing of the slab pipeline
+__device__ __forceinline__ unsigned mm_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mm_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mm_mb_init(unsigned addr, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mm_mb_expect_tx(unsigned addr, unsigned bytes) {
+  asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mm_mb_arrive(unsigned addr) {
+  asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mm_mb_wait(unsigned addr, unsigned parity) {
+  asm volatile("{\n .reg .pred p;\n MMW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra MMW;\n}" ::"r"(addr), "r"(parity) : "memory");
+}
+
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -61,7 +80,7 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 
 // XMODE 1: O = 8*q + 1, the last output row is accumulated with DFMA on the B-fragment layout (LTimes, M = 25)
 // XMODE 2: K = 4*nkc4 + 1, the last reduction row is added with DFMA on the C-fragment layout (LPlusTimes, M = 25)
-template <int QP, int NB, int XMODE, int MMA_STAGES>
+template <int QP, int NB, int XMODE, int MMA_STAGES, bool TMA>
 __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(const MomentsDescK *__restrict__ descs, MmaGeom gm) {
   extern __shared__ __align__(16) double msm[];
   constexpr int NT = 64 * NB, NTP = NT + 4;  // row stride = 4 (mod 16) doubles: conflict-free B fragments
@@ -124,13 +143,56 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
   const int my_tiles = ((long long)blockIdx.x < ntiles) ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   const int nitems = my_tiles * nst;
 
-  // producer cursor: next slab to fetch
-  int i_left = nitems, i_st = 0, i_tn = (int)(blockIdx.x % gm.ntn), i_b = (int)(blockIdx.x / gm.ntn), i_buf = 0;
+  // Slab pipeline: the rows of a slab ([KC rows][NT columns], one contiguous NT*8-byte run of the streamed field
+  // each) are fetched by TMA bulk copies -- measured: per-lane cp.async (LDGSTS) saturates near 3.8 TB/s on this
+  // part, the bulk-copy engine does not -- into MMA_STAGES buffers guarded by full/empty mbarriers.  Warp 0 is
+  // the producer (lane r issues row r) in between its own tiles; every warp releases a buffer after its last read.
+  // Rows beyond K in the last slab are not copied: their weights are zero and the stale (finite) contents of the
+  // buffer contribute nothing; columns beyond N are not copied and never stored.
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(wx + (XMODE == 1 ? (size_t)gm.nst * KC : XMODE == 2 ? (size_t)8 * q : 0));
+  const unsigned full0 = mm_smem(bars), empty0 = full0 + 8u * MMA_STAGES;
+  if (TMA) {
+    if (threadIdx.x < MMA_STAGES) { mm_mb_init(full0 + 8u * threadIdx.x, 1u); mm_mb_init(empty0 + 8u * threadIdx.x, 8u); }
+    for (int i = threadIdx.x; i < MMA_STAGES * KC * NTP; i += 256) slab[i] = 0.0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the zero fill is ordered before the async-proxy writes
+    __syncthreads();
+  }
+  int i_left = nitems, i_st = 0, i_tn = (int)(blockIdx.x % gm.ntn), i_b = (int)(blockIdx.x / gm.ntn), i_buf = 0, i_use = 0;
+  const unsigned slab0 = mm_smem(slab);
+  auto issue = [&]() {  // warp 0 only
+    if (i_left > 0) {
+      if (i_use >= MMA_STAGES) mm_mb_wait(empty0 + 8u * i_buf, ((unsigned)(i_use / MMA_STAGES) - 1u) & 1u);
+      const long long n0 = (long long)i_tn * NT;
+      const long long rem = gm.N - n0;
+      const unsigned rowbytes = (unsigned)((rem < NT ? rem : NT) * 8);
+      const long long boff = (long long)i_b * gm.in_b + n0;
+      unsigned nvalid = 0;
+      for (int r = lane; r < KC; r += 32) nvalid += (inrow[i_st * KC + r] != nullptr);
+      nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+      if (lane == 0) mm_mb_expect_tx(full0 + 8u * i_buf, nvalid * rowbytes);
+      __syncwarp();
+      for (int r = lane; r < KC; r += 32) {
+        const double *base = inrow[i_st * KC + r];
+        if (base) mm_bulk_g2s(slab0 + (unsigned)((i_buf * KC + r) * NTP) * 8u, base + boff, rowbytes, full0 + 8u * i_buf);
+      }
+      --i_left;
+      ++i_use;
+      if (++i_st == nst) {
+        i_st = 0;
+        i_tn += gridDim.x;
+        while (i_tn >= ntn) { i_tn -= ntn; ++i_b; }
+      }
+      if (++i_buf == MMA_STAGES) i_buf = 0;
+    }
+  };
+
+  // K-streamed regime (many slabs per tile): per-warp cp.async pipelines, no coupling between the warps of a CTA
   // every warp copies and consumes only its own 8*NB columns of a slab: no CTA-wide barrier in the pipeline
   constexpr int PW = 4 * NB, RPW = 32 / PW;  // 16-byte pieces per row per warp, rows per warp instruction
   const int c2 = lane % PW, r0 = lane / PW;
   const int wcol0 = warp * 8 * NB;
-  auto issue = [&]() {
+  auto issue_cp = [&]() {
     if (i_left > 0) {
       double *dst = slab + (size_t)i_buf * KC * NTP + wcol0 + 2 * c2 + (size_t)r0 * NTP;
       const long long n = (long long)i_tn * NT + wcol0 + 2 * c2;
@@ -154,8 +216,15 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
     if (++i_buf == MMA_STAGES) i_buf = 0;
   };
 
+  if (TMA) {
+    if (warp == 0) {
 #pragma unroll
-  for (int s = 0; s < MMA_STAGES - 1; ++s) issue();
+      for (int s = 0; s < MMA_STAGES - 1; ++s) issue();
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < MMA_STAGES - 1; ++s) issue_cp();
+  }
 
   double acc[QP][NB][2];
   double px[NB];  // XMODE 1: partial sums of the extra output row (this lane's k residue class)
@@ -164,9 +233,14 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
   int st = 0, tn = (int)(blockIdx.x % gm.ntn), b = (int)(blockIdx.x / gm.ntn), cbuf = 0;
 
   for (int item = 0; item < nitems; ++item) {
-    cp_async_wait<MMA_STAGES - 2>();
-    __syncwarp();  // this warp's columns of slab `item` have landed; its columns of slab item-1 are free
-    issue();
+    if (TMA) {
+      if (warp == 0) issue();  // refills the buffer every warp released after slab item-1
+      mm_mb_wait(full0 + 8u * cbuf, (unsigned)(item / MMA_STAGES) & 1u);  // slab `item` has landed
+    } else {
+      cp_async_wait<MMA_STAGES - 2>();
+      __syncwarp();  // this warp's columns of slab `item` have landed; its columns of slab item-1 are free
+      issue_cp();
+    }
 
     const double *buf = slab + (size_t)cbuf * KC * NTP;
     const int kc_lo = st * (KC / 4);
@@ -273,6 +347,10 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
         }
       }
     }
+    if (TMA) {
+      __syncwarp();
+      if (lane == 0) mm_mb_arrive(empty0 + 8u * cbuf);  // this warp is done with the buffer
+    }
     if (++cbuf == MMA_STAGES) cbuf = 0;
     if (++st == nst) {
       st = 0;
@@ -280,20 +358,20 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
       while (tn >= ntn) { tn -= ntn; ++b; }
     }
   }
-  cp_async_wait<0>();
+  if (!TMA) cp_async_wait<0>();
 }
 
 }  // namespace kb200
 
 using namespace kb200;
 
-template <int QP, int NB, int XMODE, int MMA_STAGES>
-static int launch_mma(const MomentsDescK *d_views, int n, const MmaGeom &gm, cudaStream_t st) {
+template <int QP, int NB, int XMODE, int MMA_STAGES, bool TMA>
+static int launch_mma_t(const MomentsDescK *d_views, int n, const MmaGeom &gm, cudaStream_t st) {
   constexpr int NT = 64 * NB, NTP = NT + 4;
   const size_t smem = ((size_t)gm.nkc4 * gm.q * 32 + (size_t)MMA_STAGES * gm.KC * NTP + (size_t)gm.nst * gm.KC + 8 * gm.q + 8 +
-                       (XMODE == 1 ? (size_t)gm.nst * gm.KC : XMODE == 2 ? (size_t)8 * gm.q : 0)) * sizeof(double);
+                       (XMODE == 1 ? (size_t)gm.nst * gm.KC : XMODE == 2 ? (size_t)8 * gm.q : 0) + 2 * MMA_STAGES) * sizeof(double);
   if (smem > 200 * 1024) return -1;
-  auto k = moments_mma_kernel<QP, NB, XMODE, MMA_STAGES>;
+  auto k = moments_mma_kernel<QP, NB, XMODE, MMA_STAGES, TMA>;
   KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long ntiles = gm.B * gm.ntn;
   int per_sm = (int)((220 * 1024) / (smem + 1024));
@@ -305,6 +383,17 @@ static int launch_mma(const MomentsDescK *d_views, int n, const MmaGeom &gm, cud
   dim3 grid((unsigned)ctas, n, 1);
   k<<<grid, 256, smem, st>>>(d_views, gm);
   return post_launch("moments_mma");
+}
+
+// One slab per tile (K resident, LPlusTimes): TMA bulk rows + CTA-level mbarriers (measured 6.4 -> 6.0 ms at config 2);
+// many slabs per tile (K streamed, LTimes): the per-warp cp.async pipelines are faster (6.8 vs 8.7 ms), the CTA-level
+// hand-off of a TMA pipeline costs more than the copy engine saves.
+template <int QP, int NB, int XMODE, int MMA_STAGES>
+static int launch_mma(const MomentsDescK *d_views, int n, const MmaGeom &gm, cudaStream_t st) {
+  const char *env = getenv("KB200_MOMENTS_TMA");
+  const bool tma = env ? env[0] == '1' : (gm.nst == 1 && gm.K <= 32);
+  if (tma) return launch_mma_t<QP, NB, XMODE, MMA_STAGES, true>(d_views, n, gm, st);
+  return launch_mma_t<QP, NB, XMODE, MMA_STAGES, false>(d_views, n, gm, st);
 }
 
 // Returns 0 if handled, -1 if this path does not apply (caller falls back to the DFMA kernels), >0 on error.

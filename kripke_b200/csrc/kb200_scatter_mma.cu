@@ -41,11 +41,12 @@ __device__ __forceinline__ void sc_dmma884(double &c0, double &c1, double a, dou
 }
 
 constexpr int SC_STAGES = 3;
-constexpr int SC_QP = 4, SC_NB = 2, SC_NT = 64 * SC_NB, SC_NTP = SC_NT + 4;
+constexpr int SC_NB = 2, SC_NT = 64 * SC_NB, SC_NTP = SC_NT + 4;  // QP (o-tiles of 8 destination groups per CTA) is a template parameter
 
+template <int QP>
 __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scattering_desc *__restrict__ descs, ScatGeom gm) {
   extern __shared__ __align__(16) double ssm[];
-  constexpr int QP = SC_QP, NB = SC_NB, NT = SC_NT, NTP = SC_NTP;
+  constexpr int NB = SC_NB, NT = SC_NT, NTP = SC_NTP;
   constexpr int PPR = NT / 2, RPP = 256 / PPR;
   const kb200_scattering_desc &ds = descs[blockIdx.y];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -240,10 +241,12 @@ int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_d
   const Strides3 ms = strides_dgz(layout, gm.M, gm.Gs, gm.Zs);
   gm.in_b = ms.a; gm.in_r = ms.g;
   gm.ntn = (gm.Zs + SC_NT - 1) / SC_NT;
-  const size_t smem = ((size_t)3 * gm.nkc4 * SC_QP * 32 + (size_t)SC_STAGES * gm.KC * SC_NTP + (size_t)gm.nst * gm.KC) * sizeof(double);
+  const int QP = (gm.O <= 16) ? 2 : 4;  // narrow group sets (16 groups) would waste half of a 4-tile CTA on zero padding
+  const size_t smem = ((size_t)3 * gm.nkc4 * QP * 32 + (size_t)SC_STAGES * gm.KC * SC_NTP + (size_t)gm.nst * gm.KC) * sizeof(double);
   if (smem > 200 * 1024) return -1;
-  KB_CUDA(cudaFuncSetAttribute(scatter_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int nochunks = (gm.O + 8 * SC_QP - 1) / (8 * SC_QP);
+  if (QP == 2) KB_CUDA(cudaFuncSetAttribute(scatter_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else KB_CUDA(cudaFuncSetAttribute(scatter_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nochunks = (gm.O + 8 * QP - 1) / (8 * QP);
   const long long ntiles = (long long)gm.M * gm.ntn;
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
@@ -252,6 +255,7 @@ int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_d
   if (ctas < 1) ctas = 1;
   if (ctas > ntiles) ctas = ntiles;
   dim3 grid((unsigned)ctas, n, nochunks);
-  scatter_mma_kernel<<<grid, 256, smem, st>>>((const kb200_scattering_desc *)d_descs, gm);
+  if (QP == 2) scatter_mma_kernel<2><<<grid, 256, smem, st>>>((const kb200_scattering_desc *)d_descs, gm);
+  else scatter_mma_kernel<4><<<grid, 256, smem, st>>>((const kb200_scattering_desc *)d_descs, gm);
   return post_launch("scatter_mma");
 }
