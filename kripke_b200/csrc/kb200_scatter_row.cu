@@ -1,4 +1,4 @@
-// Scattering for the moment-fastest storage orders (GZD, ZGD), default arithmetic.
+// Scattering for the storage orders whose zone index is not the fastest one (GZD, ZGD; DZG, ZDG), default arithmetic.
 //
 // In these nestings phi[.][.][nm] has the moment index fastest, so the group-to-group contraction
 // (Kernel/Scattering.cpp:73-99) would have to gather its operand with a 200-byte stride.  The moments
@@ -88,7 +88,12 @@ int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_d
 // Returns 0 if handled, -1 if this path does not apply (caller falls back to the DFMA kernel), >0 on error.
 int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, cudaStream_t st) {
   const int layout = h[0].layout;
-  if (layout != 3 && layout != 5) return -1;
+  if (layout != 1 && layout != 3 && layout != 4 && layout != 5) return -1;
+  // group-fastest nestings (DZG, ZDG) go through the generic layout transform, which cannot fold a "+="
+  const bool generic = (layout == 1 || layout == 4);
+  if (generic)
+    for (int i = 0; i < n; ++i)
+      if (h[i].accumulate) return -1;
   const char *env = getenv("KB200_SCATTER_DFMA");
   if (env && env[0] == '1') return -1;
   const int M = h[0].M, Gs = h[0].Gs, Zs = h[0].Zs;
@@ -108,8 +113,12 @@ int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, cudaStream_t st
   if (smem > 48 * 1024) return -1;
   const dim3 grid((Zs + TRZ - 1) / TRZ, Gs, 1);
   for (auto &kv : src_index) {
-    moments_transpose_kernel<true><<<grid, 256, smem, st>>>(kv.first, bufs[kv.second], M, Gs, Zs, ms.g, ms.z, 0);
-    rc = post_launch("moments_transpose");
+    if (generic) {
+      rc = kb200_layout_transform(layout, 0, M, Gs, Zs, kv.first, bufs[kv.second], st);
+    } else {
+      moments_transpose_kernel<true><<<grid, 256, smem, st>>>(kv.first, bufs[kv.second], M, Gs, Zs, ms.g, ms.z, 0);
+      rc = post_launch("moments_transpose");
+    }
     if (rc) return rc;
   }
   std::vector<kb200_scattering_desc> t(h, h + n);
@@ -125,8 +134,12 @@ int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, cudaStream_t st
   rc = kb200_scatter_mma_try(t.data(), n, d, layout, st);
   if (rc != 0) return rc < 0 ? -1 : rc;
   for (int i = 0; i < n; ++i) {
-    moments_transpose_kernel<false><<<grid, 256, smem, st>>>(bufs[nsrc + i], h[i].phi_out, M, Gs, Zs, ms.g, ms.z, h[i].accumulate);
-    rc = post_launch("moments_transpose");
+    if (generic) {
+      rc = kb200_layout_transform(0, layout, M, Gs, Zs, bufs[nsrc + i], h[i].phi_out, st);
+    } else {
+      moments_transpose_kernel<false><<<grid, 256, smem, st>>>(bufs[nsrc + i], h[i].phi_out, M, Gs, Zs, ms.g, ms.z, h[i].accumulate);
+      rc = post_launch("moments_transpose");
+    }
     if (rc) return rc;
   }
   return 0;

@@ -38,7 +38,7 @@ namespace kb200 {
 constexpr int IROW_RING = 2;   // slots of the k-face ring between neighbouring warps
 constexpr int IROW_PD = 2;     // prefetch distance in row steps
 constexpr int IROW_NS = IROW_PD + 1;  // staging slots per warp
-constexpr int IROW_MAXW = 16, IROW_MAXT = IROW_MAXW * 32;  // warps per CTA: up to 128 registers per thread
+constexpr int IROW_MAXW = 16, IROW_MAXT = IROW_MAXW * 32;  // warps per CTA: up to 128 registers per thread (22 warps x 80 registers spill)
 // per warp and staging slot: the rhs rows and the sigt rows of the warp's ER elements in memory order (1 KB each)
 // (+ one row of zone volumes, shared by the ER segments, when the population sum is fused in)
 constexpr int IROW_STAGE_BYTES = 1024 + 1024, IROW_STAGE_BYTES_POP = IROW_STAGE_BYTES + 1024;
