@@ -324,6 +324,8 @@ def main():
                              "algorithmic_bytes": alg[dom] / n_gpus,
                              "peak_source": peak_src},
                 "per_kernel": per_kernel,
+                "per_step_ms": [sum(ktime[k][i] for k in kernels) for i in range(len(ktime[kernels[0]]))],
+                "sweep_ms_per_step": list(ktime["SweepSolver"]),
                 "particles_last": particles[-1] if particles else None,
                 "wall_ms_per_step_device_region": 1e3 * wall_dev / args.steps}
         if n_gpus == 1 and not args.no_cpu_baseline:

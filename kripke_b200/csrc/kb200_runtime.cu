@@ -5,6 +5,9 @@
 // Core::FieldStorage (src/Kripke/Core/Field.h:61-104), Kernel::kConst/kCopy (src/Kripke/Kernel.h:37-81)
 // and the MPI calls of ParallelComm (src/Kripke/ParallelComm.cpp:61-251).
 #include "kb200_common.cuh"
+#include <unordered_map>
+#include <vector>
+#include <mutex>
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -245,10 +248,13 @@ int kb200_init(int device) {
   return 0;
 }
 
+namespace { void clear_pool(); }
+
 int kb200_finalize(void) {
   if (g_device < 0) return 0;
   cudaDeviceSynchronize();
   clear_desc_cache();
+  clear_pool();
   if (g_nccl.comm) {
     g_nccl.CommDestroy(g_nccl.comm);
     g_nccl.comm = nullptr;
@@ -279,16 +285,72 @@ int kb200_device_info(char *name, size_t name_len, int *sms, int *maj, int *min,
   return 0;
 }
 
+// Small allocation pool: fields that live for one SweepSolver call (the block-Jacobi "old" planes, src/Kripke/
+// ParallelComm/BlockJacobiComm.cpp:26-44) would otherwise pay a cudaMalloc + a synchronising cudaFree per chunk and
+// iteration (measured: 14-30 ms per iteration at 16 subdomains).  Blocks up to kPoolMaxBlock are kept by exact size
+// and handed out again; all work runs on the library's stream, so reuse is stream-ordered.
+namespace {
+constexpr size_t kPoolMaxBlock = 64u << 20, kPoolMaxTotal = 4ull << 30;
+std::mutex g_pool_mutex;
+std::unordered_map<void *, size_t> g_pool_sizes;            // live blocks that may be pooled when freed
+std::unordered_map<size_t, std::vector<void *>> g_pool_free;
+size_t g_pool_bytes = 0;
+void clear_pool() {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  for (auto &kv : g_pool_free)
+    for (void *q : kv.second) cudaFree(q);
+  g_pool_free.clear();
+  g_pool_sizes.clear();
+  g_pool_bytes = 0;
+}
+}  // namespace
+
 int kb200_alloc(size_t bytes, void **p) {
   KB_REQUIRE(p, "kb200_alloc: null argument");
   KB_REQUIRE(g_device >= 0, "kb200_alloc: call kb200_init first");
   *p = nullptr;
   if (bytes == 0) bytes = 16;
-  KB_CUDA(cudaMalloc(p, bytes));
+  if (bytes <= kPoolMaxBlock) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    auto it = g_pool_free.find(bytes);
+    if (it != g_pool_free.end() && !it->second.empty()) {
+      *p = it->second.back();
+      it->second.pop_back();
+      g_pool_bytes -= bytes;
+      g_pool_sizes[*p] = bytes;
+      return 0;
+    }
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation) {  // give the pooled blocks back and retry once
+    cudaGetLastError();
+    cudaDeviceSynchronize();
+    clear_pool();
+    e = cudaMalloc(p, bytes);
+  }
+  KB_CUDA(e);
+  if (bytes <= kPoolMaxBlock) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    g_pool_sizes[*p] = bytes;
+  }
   return 0;
 }
 int kb200_free(void *p) {
-  if (p) KB_CUDA(cudaFree(p));
+  if (!p) return 0;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    auto it = g_pool_sizes.find(p);
+    if (it != g_pool_sizes.end()) {
+      const size_t bytes = it->second;
+      g_pool_sizes.erase(it);
+      if (g_pool_bytes + bytes <= kPoolMaxTotal) {
+        g_pool_free[bytes].push_back(p);
+        g_pool_bytes += bytes;
+        return 0;
+      }
+    }
+  }
+  KB_CUDA(cudaFree(p));
   return 0;
 }
 int kb200_alloc_host(size_t bytes, void **p) {
