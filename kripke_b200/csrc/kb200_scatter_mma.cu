@@ -40,11 +40,33 @@ __device__ __forceinline__ void sc_dmma884(double &c0, double &c1, double a, dou
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// Volume fraction of each of the three materials in every zone of every descriptor: frac[(desc*3 + m)*Zs + z].
+// The mixture tables are walked ONCE per call here (three dependent loads per zone) instead of once per (moment,
+// zone tile) inside the contraction, where that latency chain was as long as the tile's tensor-core work.
+__global__ void scatter_fractions_kernel(const kb200_scattering_desc *__restrict__ descs, int Zs, double *__restrict__ frac) {
+  const kb200_scattering_desc &ds = descs[blockIdx.y];
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= Zs) return;
+  double f[3] = {0.0, 0.0, 0.0};
+  const int m0 = ds.zone_to_mixelem[z], nmix = ds.zone_to_num_mixelem[z];
+  for (int k = 0; k < nmix; ++k) {
+    const int mat = ds.mixelem_to_material[m0 + k];
+    const double fr = ds.mixelem_to_fraction[m0 + k];
+    if (mat == 0) f[0] += fr; else if (mat == 1) f[1] += fr; else f[2] += fr;
+  }
+  double *o = frac + (size_t)blockIdx.y * 3 * Zs + z;
+  o[0] = f[0]; o[(size_t)Zs] = f[1]; o[2 * (size_t)Zs] = f[2];
+}
+
+static double *g_frac_scratch = nullptr;
+static size_t g_frac_doubles = 0;
+
 constexpr int SC_STAGES = 3;
 constexpr int SC_NB = 2, SC_NT = 64 * SC_NB, SC_NTP = SC_NT + 4;  // QP (o-tiles of 8 destination groups per CTA) is a template parameter
 
 template <int QP>
-__global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scattering_desc *__restrict__ descs, ScatGeom gm) {
+__global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scattering_desc *__restrict__ descs, ScatGeom gm,
+                                                              const double *__restrict__ fractions) {
   extern __shared__ __align__(16) double ssm[];
   constexpr int NB = SC_NB, NT = SC_NT, NTP = SC_NTP;
   constexpr int PPR = NT / 2, RPP = 256 / PPR;
@@ -138,12 +160,8 @@ __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scatter
         const int z = tn * NT + ncol0 + 8 * nb + (lane >> 2);
         frac[0][nb] = frac[1][nb] = frac[2][nb] = 0.0;
         if (z < gm.Zs) {
-          const int m0 = ds.zone_to_mixelem[z], nmix = ds.zone_to_num_mixelem[z];
-          for (int k = 0; k < nmix; ++k) {
-            const int mat = ds.mixelem_to_material[m0 + k];
-            const double fr = ds.mixelem_to_fraction[m0 + k];
-            if (mat == 0) frac[0][nb] += fr; else if (mat == 1) frac[1][nb] += fr; else frac[2][nb] += fr;
-          }
+          const double *fz = fractions + (size_t)blockIdx.y * 3 * gm.Zs + z;
+          frac[0][nb] = __ldg(fz); frac[1][nb] = __ldg(fz + gm.Zs); frac[2][nb] = __ldg(fz + 2 * (size_t)gm.Zs);
         }
 #pragma unroll
         for (int m = 0; m < 3; ++m)
@@ -254,8 +272,20 @@ int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_d
   long long ctas = (long long)sm_count() * per_sm / ((long long)n * nochunks);
   if (ctas < 1) ctas = 1;
   if (ctas > ntiles) ctas = ntiles;
+  // per-zone material fractions of every descriptor (scratch kept between calls)
+  const size_t need = (size_t)n * 3 * gm.Zs;
+  if (g_frac_doubles < need) {
+    if (g_frac_scratch) { KB_CUDA(cudaDeviceSynchronize()); cudaFree(g_frac_scratch); g_frac_scratch = nullptr; }
+    KB_CUDA(cudaMalloc(&g_frac_scratch, need * sizeof(double)));
+    g_frac_doubles = need;
+  }
+  scatter_fractions_kernel<<<dim3((gm.Zs + 255) / 256, n, 1), 256, 0, st>>>((const kb200_scattering_desc *)d_descs, gm.Zs, g_frac_scratch);
+  {
+    int rc = post_launch("scatter_fractions");
+    if (rc) return rc;
+  }
   dim3 grid((unsigned)ctas, n, nochunks);
-  if (QP == 2) scatter_mma_kernel<2><<<grid, 256, smem, st>>>((const kb200_scattering_desc *)d_descs, gm);
-  else scatter_mma_kernel<4><<<grid, 256, smem, st>>>((const kb200_scattering_desc *)d_descs, gm);
+  if (QP == 2) scatter_mma_kernel<2><<<grid, 256, smem, st>>>((const kb200_scattering_desc *)d_descs, gm, g_frac_scratch);
+  else scatter_mma_kernel<4><<<grid, 256, smem, st>>>((const kb200_scattering_desc *)d_descs, gm, g_frac_scratch);
   return post_launch("scatter_mma");
 }
