@@ -176,28 +176,28 @@ __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scatter
     const double *buf = slab + (size_t)cbuf * KC * NTP;
     const int kc_lo = st * (KC / 4);
     const int nkc = min(gm.nkc4 - kc_lo, KC / 4);
-    const double *brow = buf + (size_t)(lane & 3) * NTP + ncol0 + (lane >> 2);
-    for (int kc = 0; kc < nkc; ++kc, brow += 4 * NTP) {
-      double bf[NB];
+    const double *brow0 = buf + (size_t)(lane & 3) * NTP + ncol0 + (lane >> 2);
+    // one pass over the slab per material present in this warp's columns (one pass for pure blocks, which is
+    // nearly all of them): no branches inside the k loop; absent columns carry a zero fraction
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb) bf[nb] = brow[8 * nb];
+    for (int m = 0; m < 3; ++m) {
+      if (!((present >> m) & 0x9u)) continue;  // warp-uniform
+      const double *wf = Ws + (((size_t)m * gm.nkc4 + kc_lo) * QP) * 32 + lane;
+      const double *brow = brow0;
+      double fm[NB];
 #pragma unroll
-      for (int m = 0; m < 3; ++m) {
-        const unsigned mm = (present >> m) & 0x9u;  // bit0: nb 0, bit3: nb 1
-        if (mm) {
-          const double *wf = Ws + (((size_t)m * gm.nkc4 + kc_lo + kc) * QP) * 32 + lane;
-          double af[QP];
+      for (int nb = 0; nb < NB; ++nb) fm[nb] = frac[m][nb];
+#pragma unroll 4
+      for (int kc = 0; kc < nkc; ++kc, brow += 4 * NTP, wf += QP * 32) {
+        double af[QP], bm[NB];
 #pragma unroll
-          for (int a = 0; a < QP; ++a) af[a] = wf[a * 32];
+        for (int nb = 0; nb < NB; ++nb) bm[nb] = brow[8 * nb] * fm[nb];
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb) {
-            if (mm & (1u << (3 * nb))) {
-              const double bm = bf[nb] * frac[m][nb];
+        for (int a = 0; a < QP; ++a) af[a] = wf[a * 32];
 #pragma unroll
-              for (int a = 0; a < QP; ++a) sc_dmma884(acc[a][nb][0], acc[a][nb][1], af[a], bm);
-            }
-          }
-        }
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+          for (int a = 0; a < QP; ++a) sc_dmma884(acc[a][nb][0], acc[a][nb][1], af[a], bm[nb]);
       }
     }
 
