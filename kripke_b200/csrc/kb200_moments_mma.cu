@@ -426,6 +426,13 @@ int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, i
     gm.ntn = (gm.N + 127) / 128;
     if (gm.q == 4 && gm.O == 25) {  // 3 tensor-core tiles + one DFMA row instead of 4 tiles (22% less fp64 work)
       gm.q = 3;
+      const char *e = getenv("KB200_LTIMES_KC");
+      const int kc = e ? atoi(e) : 32;
+      if (kc == 32 && Kp >= 64) {  // 32-row slabs, two stages: the per-slab bookkeeping (~200 instructions) is amortised over 48 DMMAs
+        gm.KC = 32;
+        gm.nst = (Kp + gm.KC - 1) / gm.KC;
+        return launch_mma<3, 2, 1, 2>(dv, n, gm, st);
+      }
       return launch_mma<3, 2, 1, 3>(dv, n, gm, st);
     }
     if (gm.q <= 4) return launch_mma<4, 2, 0, 3>(dv, n, gm, st);
