@@ -199,11 +199,20 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
       const bool ncol = n < gm.N;
       const long long boff = (long long)i_b * gm.in_b + n;
       const double *const *rp = inrow + i_st * KC + r0;
+      // interior slabs (every row exists, every column inside the run): plain 16-byte copies, no predicates
+      const bool interior = ((i_st + 1) * KC <= K) && ((long long)(i_tn + 1) * NT <= gm.N);
+      if (interior) {
+        const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
+#pragma unroll 8
+        for (int r = r0, o = 0; r < KC; r += RPW, rp += RPW, o += RPW * NTP * 8)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32 + o), "l"(*rp + boff) : "memory");
+      } else {
 #pragma unroll 4
-      for (int r = r0; r < KC; r += RPW, rp += RPW, dst += (size_t)RPW * NTP) {
-        const double *base = *rp;
-        const bool valid = ncol && base != nullptr;
-        cp_async16_zfill(dst, valid ? base + boff : dsc.in[0], valid);
+        for (int r = r0; r < KC; r += RPW, rp += RPW, dst += (size_t)RPW * NTP) {
+          const double *base = *rp;
+          const bool valid = ncol && base != nullptr;
+          cp_async16_zfill(dst, valid ? base + boff : dsc.in[0], valid);
+        }
       }
       --i_left;
       if (++i_st == nst) {
