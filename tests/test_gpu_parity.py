@@ -275,3 +275,37 @@ def test_layout_transform_round_trip(gpu):
         assert np.array_equal(mid, np.ascontiguousarray(cube.transpose(perm)).ravel())
     for b in bufs:
         A.kb200_free(b)
+
+
+def test_fused_population_abi_matches_separate_kernel(gpu):
+    """kb200_sweep_population + kb200_population_reduce (sum left behind by the sweep) == kb200_population on the
+    same psi, and the host layer falls back to the separate kernel as soon as psi is written by anyone else."""
+    args = "--zones 16,12,20 --groups 8 --quad 16 --legendre 1 --gset 2 --dset 8 --zset 1,1,1 --layout DGZ"
+    p, o, _, _ = pair(gpu, args)
+    fill_both(p, o, "rhs", 4100, 0.0, 1.0)
+    o.sweep_solver(False)
+    p.call("SweepSolver")
+    fused = p.call("population")          # finishes the partial sums of the sweep kernels
+    ref = o.population()
+    assert abs(fused - ref) <= RTOL * abs(ref)
+    # touching psi invalidates the cached partials: the value must follow the new contents
+    v = seeded(len(o.chunk("psi", 0)), 4200, 0.0, 1.0)
+    o.chunk("psi", 0)[:] = v
+    p.set_chunk("psi", 0, v)
+    ref2 = o.population()
+    got2 = p.call("population")
+    assert abs(got2 - ref2) <= RTOL * abs(ref2)
+    assert abs(ref2 - ref) > 1e-6 * abs(ref)
+
+
+def test_device_allocation_pool_reuses_blocks(gpu):
+    A = gpu.abi()
+    a, b = C.c_void_p(), C.c_void_p()
+    assert A.kb200_alloc(1 << 20, C.byref(a)) == 0
+    first = a.value
+    assert A.kb200_free(a) == 0
+    assert A.kb200_alloc(1 << 20, C.byref(b)) == 0
+    assert b.value == first               # same size: the pooled block comes back, no cudaMalloc
+    big = C.c_void_p()
+    assert A.kb200_alloc(96 << 20, C.byref(big)) == 0 and A.kb200_free(big) == 0   # above the pool limit: plain cudaFree
+    assert A.kb200_free(b) == 0
