@@ -238,6 +238,36 @@ __global__ void layout_transform_kernel(int src_layout, int dst_layout, int na, 
 }
 
 
+// Tiled variant for the case that source and destination differ in their fastest index: a block moves one
+// 32 x 32 tile of the (source-fastest, destination-fastest) plane through shared memory, so both the reads and
+// the writes are 256-byte rows.  ext/ss/ds: extents and source/destination strides of (f = source-fastest index,
+// d = destination-fastest index, t = the third one).
+__global__ void __launch_bounds__(256) layout_transform_tiled_kernel(int nf, int nd, int nt, long long ss_d, long long ss_t,
+                                                                     long long ds_f, long long ds_t,
+                                                                     const double *__restrict__ src, double *__restrict__ dst) {
+  __shared__ double tile[32][33];
+  const int tf = (nf + 31) / 32, td = (nd + 31) / 32;
+  const long long ntiles = (long long)tf * td * nt;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;  // 32 x 8 threads
+  for (long long b = blockIdx.x; b < ntiles; b += gridDim.x) {
+    const int t = (int)(b / ((long long)tf * td));
+    const int r = (int)(b - (long long)t * tf * td);
+    const int f0 = (r % tf) * 32, d0 = (r / tf) * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // rows of the source: f contiguous
+      const int dd = d0 + ly + 8 * k, ff = f0 + lx;
+      if (dd < nd && ff < nf) tile[ly + 8 * k][lx] = __ldg(src + (long long)t * ss_t + (long long)dd * ss_d + ff);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // rows of the destination: d contiguous
+      const int ff = f0 + ly + 8 * k, dd = d0 + lx;
+      if (ff < nf && dd < nd) dst[(long long)t * ds_t + (long long)ff * ds_f + dd] = tile[lx][ly + 8 * k];
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace kb200
 
 using namespace kb200;
@@ -366,6 +396,21 @@ int kb200_layout_transform(int src_layout, int dst_layout, int na, int ng, int n
   KB_REQUIRE(src && dst && src != dst, "kb200_layout_transform: bad pointers (out-of-place only)");
   long long total = (long long)na * ng * nz;
   if (total <= 0) return 0;
+  {  // different fastest index on the two sides: tiled transpose, both sides coalesced
+    const Strides3 a = strides_dgz(src_layout, na, ng, nz), b = strides_dgz(dst_layout, na, ng, nz);
+    const long long sst[3] = {a.a, a.g, a.z}, dst_[3] = {b.a, b.g, b.z};
+    const int ext[3] = {na, ng, nz};
+    int f = -1, d = -1;
+    for (int x = 0; x < 3; ++x) { if (sst[x] == 1) f = x; if (dst_[x] == 1) d = x; }
+    if (f >= 0 && d >= 0 && f != d) {
+      const int t = 3 - f - d;
+      const long long ntiles = (long long)((ext[f] + 31) / 32) * ((ext[d] + 31) / 32) * ext[t];
+      long long blocks = ntiles < 148LL * 64 ? ntiles : 148LL * 64;
+      layout_transform_tiled_kernel<<<(unsigned)blocks, 256, 0, resolve_stream(stream)>>>(ext[f], ext[d], ext[t], sst[d], sst[t], dst_[f],
+                                                                                        dst_[t], src, dst);
+      return post_launch("layout_transform_tiled");
+    }
+  }
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
   layout_transform_kernel<<<(unsigned)blocks, 256, 0, resolve_stream(stream)>>>(src_layout, dst_layout, na, ng, nz, src, dst);

@@ -309,3 +309,23 @@ def test_device_allocation_pool_reuses_blocks(gpu):
     big = C.c_void_p()
     assert A.kb200_alloc(96 << 20, C.byref(big)) == 0 and A.kb200_free(big) == 0   # above the pool limit: plain cudaFree
     assert A.kb200_free(b) == 0
+
+
+def test_irow_sweep_matches_line_kernel_at_full_zone_extent(gpu, monkeypatch):
+    """size-independent property at BASELINE config 2's zone extent (64^3: four k tiles of 16 planes, 16-lane rows,
+    TMA staging two rows ahead): the i-row scan kernel and the thread-per-row kernel (KB200_SWEEP_IROW=0), which is
+    bit-exact against the oracle in the small cases, must agree on psi and on all outgoing faces."""
+    args = "--zones 64,64,64 --groups 2 --quad 16 --legendre 0 --gset 1 --dset 8 --zset 1,1,1 --layout DGZ"
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("KB200_SWEEP_IROW", mode)
+        p = gpu.Problem(args)
+        for c in range(p.num_chunks("rhs")):
+            p.set_chunk("rhs", c, seeded(len(p.chunk("rhs", c)), 5000 + c, 0.0, 1.0))
+        p.call("SweepSolver")
+        res[mode] = {f: p.field(f).copy() for f in ("psi", "i_plane", "j_plane", "k_plane")}
+        res[mode]["pop"] = p.call("population")
+        p.close()
+    for f in ("psi", "i_plane", "j_plane", "k_plane"):
+        assert_close(res["1"][f], res["0"][f], f"irow vs zline {f}", False)
+    assert abs(res["1"]["pop"] - res["0"]["pop"]) <= RTOL * abs(res["0"]["pop"])
