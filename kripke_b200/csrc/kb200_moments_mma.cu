@@ -42,6 +42,10 @@ struct MmaGeom {
   long long B, N;     // batches, contiguous run
   long long in_b, in_r, out_b, out_r;  // batch / row strides of the streamed and the produced field
   long long ntn;      // tiles along n
+  // packed mode (ZDG: runs of only pack_N = Gs columns per zone): the B = Zs runs are presented as ONE virtual run of
+  // B * pack_N columns; virtual column v lives at (v / pack_N) * pack_{in,out}_b + v % pack_N
+  int pack_N;
+  long long pack_in_b, pack_out_b;
 };
 
 __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsrc, bool valid) {
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
       double *dst = slab + (size_t)i_buf * KC * NTP + wcol0 + 2 * c2 + (size_t)r0 * NTP;
       const long long n = (long long)i_tn * NT + wcol0 + 2 * c2;
       const bool ncol = n < gm.N;
-      const long long boff = (long long)i_b * gm.in_b + n;
+      const long long boff = (long long)i_b * gm.in_b + (gm.pack_N ? (n / gm.pack_N) * gm.pack_in_b + n % gm.pack_N : n);
       const double *const *rp = inrow + i_st * KC + r0;
       // interior slabs (every row exists, every column inside the run): plain 16-byte copies, no predicates
       const bool interior = ((i_st + 1) * KC <= K) && ((long long)(i_tn + 1) * NT <= gm.N);
@@ -330,8 +334,9 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
           v += __shfl_xor_sync(0xffffffffu, v, 2);
           const long long n = (long long)tn * NT + ncol0 + 8 * nb + (lane >> 2);
           if ((lane & 3) == 0 && n < gm.N) {
-            if (gm.accumulate) v += row[n];
-            row[n] = v;
+            const long long no = gm.pack_N ? (n / gm.pack_N) * gm.pack_out_b + n % gm.pack_N : n;
+            if (gm.accumulate) v += row[no];
+            row[no] = v;
           }
         }
       }
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
               const long long n = ncol + 8 * nb;
               if (n < gm.N) {
                 double2 v = make_double2(acc[a][nb][0], acc[a][nb][1]);
-                double2 *p = reinterpret_cast<double2 *>(row + n);
+                double2 *p = reinterpret_cast<double2 *>(row + (gm.pack_N ? (n / gm.pack_N) * gm.pack_out_b + n % gm.pack_N : n));
                 if (gm.accumulate) { const double2 old = *p; v.x += old.x; v.y += old.y; }
                 *p = v;
               }
@@ -400,7 +405,7 @@ static int launch_mma_t(const MomentsDescK *d_views, int n, const MmaGeom &gm, c
 template <int QP, int NB, int XMODE, int MMA_STAGES>
 static int launch_mma(const MomentsDescK *d_views, int n, const MmaGeom &gm, cudaStream_t st) {
   const char *env = getenv("KB200_MOMENTS_TMA");
-  const bool tma = env ? env[0] == '1' : (gm.nst == 1 && gm.K <= 32);
+  const bool tma = (env ? env[0] == '1' : (gm.nst == 1 && gm.K <= 32)) && gm.pack_N == 0;  // packed rows are not contiguous
   if (tma) return launch_mma_t<QP, NB, XMODE, MMA_STAGES, true>(d_views, n, gm, st);
   return launch_mma_t<QP, NB, XMODE, MMA_STAGES, false>(d_views, n, gm, st);
 }
@@ -408,7 +413,7 @@ static int launch_mma(const MomentsDescK *d_views, int n, const MmaGeom &gm, cud
 // Returns 0 if handled, -1 if this path does not apply (caller falls back to the DFMA kernels), >0 on error.
 int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, int nsets, int accumulate, const void *d_views,
                           int n, const void *const *h_ptrs, int n_ptrs, cudaStream_t st) {
-  if (layout != 0 && layout != 1 && layout != 2) return -1;
+  if (layout != 0 && layout != 1 && layout != 2 && layout != 4) return -1;
   const char *env = getenv("KB200_MOMENTS_DFMA");
   if (env && env[0] == '1') return -1;
   for (int i = 0; i < n_ptrs; ++i)
@@ -419,7 +424,13 @@ int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, i
   const Strides3 fs = strides_dgz(layout, Ds, Gs, Zs), ms = strides_dgz(layout, M, Gs, Zs);
   long long flux_b, mom_b;
   if (layout == 2) { gm.B = Gs; gm.N = Zs; flux_b = fs.g; mom_b = ms.g; }     // GDZ: batch = group
-  else { gm.B = 1; gm.N = (long long)Gs * Zs; flux_b = 0; mom_b = 0; }        // DGZ, DZG
+  else if (layout == 4) {                                                     // ZDG: runs of Gs columns per zone, packed
+    if (!(Gs % 16 == 0 && Gs <= 128 && 128 % Gs == 0)) return -1;             // a warp's 16 columns must stay inside one zone
+    gm.B = 1; gm.N = (long long)Gs * Zs; flux_b = 0; mom_b = 0;
+    gm.pack_N = Gs;
+    gm.pack_in_b = (mode == 0) ? fs.z : ms.z;
+    gm.pack_out_b = (mode == 0) ? ms.z : fs.z;
+  } else { gm.B = 1; gm.N = (long long)Gs * Zs; flux_b = 0; mom_b = 0; }      // DGZ, DZG
   if (gm.N % 2 != 0) return -1;
   if (mode == 0) { gm.O = M; gm.K = nsets * Ds; gm.in_b = flux_b; gm.in_r = fs.a; gm.out_b = mom_b; gm.out_r = ms.a; }
   else { gm.O = nsets * Ds; gm.K = M; gm.in_b = mom_b; gm.in_r = ms.a; gm.out_b = flux_b; gm.out_r = fs.a; }

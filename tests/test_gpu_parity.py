@@ -329,3 +329,20 @@ def test_irow_sweep_matches_line_kernel_at_full_zone_extent(gpu, monkeypatch):
     for f in ("psi", "i_plane", "j_plane", "k_plane"):
         assert_close(res["1"][f], res["0"][f], f"irow vs zline {f}", False)
     assert abs(res["1"]["pop"] - res["0"]["pop"]) <= RTOL * abs(res["0"]["pop"])
+
+
+@pytest.mark.parametrize("legendre,quad", [(4, 96), (2, 16)])
+def test_moments_tensor_core_packed_zdg(gpu, legendre, quad):
+    """ZDG (group fastest): runs of Gs = 16 columns per zone are packed eight to a 128-column tile of kb200_moments_mma.cu"""
+    args = f"--zones 10,6,8 --groups 32 --quad {quad} --legendre {legendre} --gset 2 --dset 8 --zset 1,2,1 --layout ZDG"
+    p, o, _, _ = pair(gpu, args)
+    fill_both(p, o, "psi", 6100, -1.0, 2.0)
+    o.zero("phi"); o.ltimes()
+    p.call("zero:phi"); p.call("LTimes")
+    assert_close(p.field("phi"), o.field("phi"), "LTimes packed ZDG", False)
+    fill_both(p, o, "phi_out", 6200, -1.0, 1.0)
+    o.zero("rhs"); o.lplustimes()
+    p.call("zero:rhs"); p.call("LPlusTimes")
+    assert_close(p.field("rhs"), o.field("rhs"), "LPlusTimes packed ZDG", False)
+    o.ltimes(); p.call("LTimes")  # accumulate on top
+    assert_close(p.field("phi"), o.field("phi"), "LTimes accumulate packed ZDG", False)
