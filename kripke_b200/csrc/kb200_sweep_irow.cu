@@ -32,6 +32,7 @@
 // When pop_partial is non-null the kernel also accumulates Kernel::population's sum
 // (w(d)*psi)*volume(z) (src/Kripke/Kernel/Population.cpp:49-63) while psi is still in registers.
 #include "kb200_common.cuh"
+#include <type_traits>
 
 namespace kb200 {
 
@@ -47,6 +48,7 @@ struct IGeom {  // kernel parameter: lives in the constant bank, costs no regist
   int layout, Ds, Gs, ni, nj, nk;
   int NW, nkt;  // warps (= k-planes) per CTA, k tiles
   int E, ngroups;
+  unsigned sb, vol_off;  // bytes of one staging slot and offset of the zone-volume rows in it
   unsigned sa, sg, Zs, ipd, ipg, jpd, jpg, kpd, kpg;  // element strides: psi/rhs (direction, group), zones, planes
 };
 
@@ -158,11 +160,14 @@ __device__ __forceinline__ IItem irow_item(const IGeom &gm, int gi, int t, int w
   return it;
 }
 
-template <int LR, bool FWD, bool UNI, bool POP>
+// PAIR: rows j and j+1 of a k-plane are adjacent in memory, so with an even nj one bulk copy per array brings in
+// TWO rows: half as many copy/mbarrier sequences per zone, two staging slots of a row pair each.
+template <int LR, bool FWD, bool UNI, bool POP, bool PAIR>
 __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGeom &gm, const IShared &sh,
                                            const double *__restrict__ wq, const double *__restrict__ vol) {
-  constexpr int R = IROW_RING, PD = IROW_PD, NS = IROW_NS;
-  constexpr unsigned SB = POP ? IROW_STAGE_BYTES_POP : IROW_STAGE_BYTES;
+  constexpr int R = IROW_RING, PD = IROW_PD, NS = PAIR ? 2 : IROW_NS;
+  constexpr unsigned RB = PAIR ? 2048u : 1024u;  // bytes of the row block(s) of a warp's ER segments in one slot
+  const unsigned SB = gm.sb;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int seg = lane / LR, ls = lane % LR;
   const int NW = gm.NW, ni = gm.ni, nj = gm.nj, nk = gm.nk, nkt = gm.nkt;
@@ -174,9 +179,9 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
 
   const unsigned rowb = 8u * (unsigned)ni;                                  // bytes of one i-row
   const unsigned stage0 = sh.stage + (unsigned)(w * NS) * SB;               // + slot * SB : [rhs rows of the ER segments][sigt rows]
-  const unsigned kin0 = sh.kin;                                             // + slot * 1024 (warp 0): k_plane rows of the ER segments
+  const unsigned kin0 = sh.kin;                                             // + slot * RB (warp 0): k_plane rows of the ER segments
   const unsigned sbar0 = sh.sbar + 8u * (unsigned)(w * NS);                 // + 8 * slot
-  const unsigned mine = (unsigned)seg * rowb + 8u * i0;                     // this lane's four zones inside a staged row block
+  const unsigned mine = (unsigned)seg * (PAIR ? 2u : 1u) * rowb + 8u * i0;   // this lane's four zones inside a staged row block
   const unsigned fk_in0 = sh.fkx + (unsigned)w * 1024u + 16u * lane;                       // + ring slot * (NW+1)*1024
   const unsigned fkx_slot = (unsigned)(NW + 1) * 1024u;
   const unsigned full_in = sh.full + 8u * (unsigned)(w * R), full_out = full_in + 8u * R;
@@ -208,18 +213,38 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
       const unsigned roff = (unsigned)(r * jstep);
       const unsigned dst = stage0 + sqn * SB + (unsigned)seg * rowb;
       ir_bulk_g2s(dst, ds.rhs + (it.off0 + roff), rowb, bar);
-      ir_bulk_g2s(dst + 1024, ds.sigt + (it.soff0 + roff), rowb, bar);
-      if (kload) ir_bulk_g2s(kin0 + sqn * 1024u + (unsigned)seg * rowb, ds.k_plane + (it.kpx0 + roff), rowb, bar);
+      ir_bulk_g2s(dst + RB, ds.sigt + (it.soff0 + roff), rowb, bar);
+      if (kload) ir_bulk_g2s(kin0 + sqn * RB + (unsigned)seg * rowb, ds.k_plane + (it.kpx0 + roff), rowb, bar);
       if (POP && lane == 0)  // the zone volumes of the row: the same for every element
-        ir_bulk_g2s(stage0 + sqn * SB + 2048, vol + (it.soff0 - (unsigned)it.g * gm.Zs + roff), rowb, bar);
+        ir_bulk_g2s(stage0 + sqn * SB + gm.vol_off, vol + (it.soff0 - (unsigned)it.g * gm.Zs + roff), rowb, bar);
+    }
+  };
+  // PAIR: rows 2*pp and 2*pp+1 (sweep order) of item `it`, whose first step is qn, as one copy per array
+  auto prefetch2 = [&](const IItem &it, int pp, bool ktile0, unsigned qn, unsigned sqn) {
+    const bool kload = (w == 0) && !(k_zero && ktile0);
+    if (w == 0 && !ktile0) ir_wait_ge(sh.prod, qn + 2u - (unsigned)nj);
+    const unsigned bar = sbar0 + 8u * sqn;
+    if (lane == 0) ir_mb_expect_tx(bar, (kload ? 3u : 2u) * 2u * rowb * (unsigned)(32 / LR) + (POP ? 2u * rowb : 0u));
+    __syncwarp();  // also: every lane is done reading the slot's previous contents
+    if (ls == 0) {
+      const unsigned roff = (unsigned)(((jd > 0) ? 2 * pp : 2 * pp + 1) * jstep);  // the lower of the two rows in memory
+      const unsigned dst = stage0 + sqn * SB + (unsigned)seg * 2u * rowb;
+      ir_bulk_g2s(dst, ds.rhs + (it.off0 + roff), 2u * rowb, bar);
+      ir_bulk_g2s(dst + RB, ds.sigt + (it.soff0 + roff), 2u * rowb, bar);
+      if (kload) ir_bulk_g2s(kin0 + sqn * RB + (unsigned)seg * 2u * rowb, ds.k_plane + (it.kpx0 + roff), 2u * rowb, bar);
+      if (POP && lane == 0) ir_bulk_g2s(stage0 + sqn * SB + gm.vol_off, vol + (it.soff0 - (unsigned)it.g * gm.Zs + roff), 2u * rowb, bar);
     }
   };
   auto next_sq = [](unsigned s, int by) { unsigned v = s + (unsigned)by; return v >= (unsigned)NS ? v - NS : v; };
 
-  // prologue: rows 0..PD-1 of the first item
+  // prologue: rows 0..PD-1 (the first row pair) of the first item
+  if (PAIR) {
+    if (nx_ok && nx.kv) prefetch2(nx, 0, true, 0u, 0u);
+  } else {
 #pragma unroll
-  for (int r = 0; r < PD; ++r)
-    if (nx_ok && nx.kv && r < nj) prefetch(nx, r, true, (unsigned)r, (unsigned)r);
+    for (int r = 0; r < PD; ++r)
+      if (nx_ok && nx.kv && r < nj) prefetch(nx, r, true, (unsigned)r, (unsigned)r);
+  }
   if (nx_ok && nx.kv && !i_zero) fi0n = ir_ld_cg(ds.i_plane + nx.ipx0);
 
   while (nx_ok) {
@@ -242,9 +267,13 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
         ++q;
         if (++slot == R) { slot = 0; ph ^= 1u; }
       }
+      if (PAIR) {  // the next item (tile 0 of the next group) starts from scratch
+        if (nx_pre) prefetch2(nx, 0, nt == 0, q, sq);
+      } else {
 #pragma unroll
-      for (int r = 0; r < PD; ++r)  // the next item (tile 0 of the next group) starts from scratch
-        if (nx_pre && r < nj) prefetch(nx, r, nt == 0, q + (unsigned)r, next_sq(sq, r));
+        for (int r = 0; r < PD; ++r)
+          if (nx_pre && r < nj) prefetch(nx, r, nt == 0, q + (unsigned)r, next_sq(sq, r));
+      }
       if (nx_pre && !i_zero) fi0n = ir_ld_cg(ds.i_plane + nx.ipx0);
       gi = ngi; t = nt;
       continue;
@@ -257,10 +286,17 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
     unsigned off = it.off0, ipx = it.ipx0;
     int jz = (jd > 0) ? 0 : nj - 1;
 
-#pragma unroll 2  // measured: 1 -> 17.0 ms, 2 -> 16.4 ms, 4 -> 21.8 ms (instruction cache) with the fused population sum
-    for (int j = 0; j < nj; ++j) {
-      // ---- loads of the row PD steps ahead ----
-      {
+    // one row step; PAR = position of the row in its pair (PAIR mode, compile time) or -1
+    auto row_step = [&](auto par_tag, const int j) {
+      constexpr int PAR = decltype(par_tag)::value;
+      // ---- loads of the row(s) PD steps ahead ----
+      if (PAIR) {
+        if (PAR == 0) {
+          const unsigned sqn = sq ^ 1u;
+          if (j + 2 < nj) prefetch2(it, j / 2 + 1, ktile0, q + 2u, sqn);
+          else if (nx_pre) prefetch2(nx, 0, nt == 0, q + 2u, sqn);
+        }
+      } else {
         const int r = j + PD;
         const unsigned sqn = next_sq(sq, PD);
         if (r < nj) prefetch(it, r, ktile0, q + (unsigned)PD, sqn);
@@ -271,14 +307,16 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
         if (j + 1 < nj) fi0n = ir_ld_cg(ds.i_plane + (ipx + (unsigned)jd));
         else if (nx_pre) fi0n = ir_ld_cg(ds.i_plane + nx.ipx0);
       }
-      ir_mb_wait(sbar0 + 8u * sq, sph);  // the bulk copies issued PD steps ago for this row have landed
+      if (!PAIR || PAR == 0) ir_mb_wait(sbar0 + 8u * sq, sph);  // the bulk copies issued for this row (pair) have landed
 
       // ---- everything that does not need the upwind k and j faces ----
-      const unsigned st = stage0 + sq * SB + mine;
+      // PAIR: the first row of the pair is the lower one in memory when sweeping up in j, the upper one otherwise
+      const unsigned prow = PAIR ? (((jd > 0) ? (unsigned)PAR : (unsigned)(PAR ^ 1)) * rowb) : 0u;
+      const unsigned st = stage0 + sq * SB + mine + prow;
       double A[4], rc[4], r4[4];
       const double cy = tyc * sh.rdy[jz];
       {
-        const double2 e = ir_lds128(st + 1024), f = ir_lds128(st + 1024 + 16);
+        const double2 e = ir_lds128(st + RB), f = ir_lds128(st + RB + 16);
         const double s4[4] = {e.x, e.y, f.x, f.y};
         const double2 a = ir_lds128(st), b = ir_lds128(st + 16);
         r4[0] = a.x; r4[1] = a.y; r4[2] = b.x; r4[3] = b.y;
@@ -319,7 +357,7 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
         } else if (k_zero && ktile0) {
           fk[0] = fk[1] = fk[2] = fk[3] = 0.0;
         } else {
-          const unsigned src = kin0 + sq * 1024u + mine;
+          const unsigned src = kin0 + sq * RB + mine + prow;
           const double2 k0 = ir_lds128(src), k1 = ir_lds128(src + 16);
           fk[0] = k0.x; fk[1] = k0.y; fk[2] = k1.x; fk[3] = k1.y;
         }
@@ -374,7 +412,7 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
       if (it.ev) {
         ir_stg256(ds.psi + (off + i0), p4);
         if (POP) {
-          const unsigned vs = stage0 + sq * SB + 2048 + 8u * i0;
+          const unsigned vs = stage0 + sq * SB + gm.vol_off + prow + 8u * i0;
           const double2 va = ir_lds128(vs), vb = ir_lds128(vs + 16);
           const double v4[4] = {va.x, va.y, vb.x, vb.y};
 #pragma unroll
@@ -400,16 +438,30 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
         if (lane == 0) ir_st_release(sh.prod, q + 1u);
       }
       ++q;
-      if (++sq == (unsigned)NS) { sq = 0; sph ^= 1u; }
+      if (PAIR) {
+        if (PAR == 1) { sq ^= 1u; if (sq == 0u) sph ^= 1u; }
+      } else {
+        if (++sq == (unsigned)NS) { sq = 0; sph ^= 1u; }
+      }
       if (++slot == R) { slot = 0; ph ^= 1u; }
       off += (unsigned)jstep; ipx += (unsigned)jd; jz += jd;
+    };
+    if (PAIR) {
+#pragma unroll 1
+      for (int j = 0; j < nj; j += 2) {
+        row_step(std::integral_constant<int, 0>{}, j);
+        row_step(std::integral_constant<int, 1>{}, j + 1);
+      }
+    } else {
+#pragma unroll 2  // measured: 1 -> 17.0 ms, 2 -> 16.4 ms, 4 -> 21.8 ms (instruction cache) with the fused population sum
+      for (int j = 0; j < nj; ++j) row_step(std::integral_constant<int, -1>{}, j);
     }
     gi = ngi; t = nt;
   }
   return pop;
 }
 
-template <int LR, bool POP>
+template <int LR, bool POP, bool PAIR>
 __global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sweep_desc *__restrict__ descs, const __grid_constant__ IGeom gm,
                                                              const double *const *__restrict__ pop_w,
                                                              const double *const *__restrict__ pop_vol,
@@ -424,8 +476,8 @@ __global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sw
   IShared sh;
   unsigned char *p = ism;
   sh.fkx = ir_smem_addr(p); p += (size_t)IROW_RING * (NW + 1) * 1024;
-  sh.kin = ir_smem_addr(p); p += (size_t)IROW_NS * 1024;
-  sh.stage = ir_smem_addr(p); p += (size_t)NW * IROW_NS * (POP ? IROW_STAGE_BYTES_POP : IROW_STAGE_BYTES);
+  sh.kin = ir_smem_addr(p); p += (size_t)4 * 1024;
+  sh.stage = ir_smem_addr(p); p += (size_t)NW * (PAIR ? 2 : IROW_NS) * gm.sb;
   double *tab = reinterpret_cast<double *>(p);
   double *cxt = tab, *txc = cxt + Ds, *tyc = txc + Ds, *tzc = tyc + Ds, *rdy = tzc + Ds, *rdz = rdy + nj;
   double *red = rdz + nk;  // [32] block reduction of the population partials
@@ -459,11 +511,11 @@ __global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sw
   const double *vol = POP ? pop_vol[blockIdx.y] : nullptr;
   double pop;
   if (uniform_x) {
-    if (ds.id > 0) pop = irow_run<LR, true, true, POP>(ds, gm, sh, wq, vol);
-    else pop = irow_run<LR, false, true, POP>(ds, gm, sh, wq, vol);
+    if (ds.id > 0) pop = irow_run<LR, true, true, POP, PAIR>(ds, gm, sh, wq, vol);
+    else pop = irow_run<LR, false, true, POP, PAIR>(ds, gm, sh, wq, vol);
   } else {
-    if (ds.id > 0) pop = irow_run<LR, true, false, POP>(ds, gm, sh, wq, vol);
-    else pop = irow_run<LR, false, false, POP>(ds, gm, sh, wq, vol);
+    if (ds.id > 0) pop = irow_run<LR, true, false, POP, PAIR>(ds, gm, sh, wq, vol);
+    else pop = irow_run<LR, false, false, POP, PAIR>(ds, gm, sh, wq, vol);
   }
 
   if (POP) {  // fixed-order block reduction: lanes, then warps
@@ -482,16 +534,16 @@ __global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sw
 
 using namespace kb200;
 
-template <int LR>
+template <int LR, bool PAIR>
 static int launch_irow(const kb200_sweep_desc *d_descs, int n, const IGeom &gm, int cps, size_t smem, const double *const *pw,
                        const double *const *pv, double *pp, cudaStream_t st) {
   dim3 grid(cps, n, 1);
   if (pp) {
-    auto k = sweep_irow_kernel<LR, true>;
+    auto k = sweep_irow_kernel<LR, true, PAIR>;
     KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, pw, pv, pp);
   } else {
-    auto k = sweep_irow_kernel<LR, false>;
+    auto k = sweep_irow_kernel<LR, false, PAIR>;
     KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, nullptr, nullptr, nullptr);
   }
@@ -537,9 +589,20 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
   // rows are fetched IROW_PD steps ahead, at most into the next item; warp 0 must not wait for tile-boundary
   // k faces of a row the last warp can only produce after warp 0 has moved on
   if (nj <= IROW_PD) return -1;
-  const size_t smem = (size_t)IROW_RING * (gm.NW + 1) * 1024 + (size_t)IROW_NS * 1024 + (size_t)gm.NW * IROW_NS * IROW_STAGE_BYTES_POP +
-                      ((size_t)4 * gm.Ds + nj + nk + 32 + 2 * (gm.NW + 1) * IROW_RING + gm.NW * IROW_NS + 2) * sizeof(double);
-  if (smem > 226 * 1024) return -1;
+  // staging layout: row pairs (two slots) when nj is even and it fits, single rows (three slots) otherwise
+  const unsigned rowb = 8u * (unsigned)ni;
+  const char *pe = getenv("KB200_IROW_PAIR");
+  bool pair = (nj % 2 == 0) && nj >= 4 && !(pe && pe[0] == '0');
+  size_t smem = 0;
+  for (;;) {
+    const unsigned rb = pair ? 2048u : 1024u;
+    gm.vol_off = 2u * rb;
+    gm.sb = gm.vol_off + (d_pop_partial ? (pair ? 2u : 1u) * rowb : 0u);
+    smem = (size_t)IROW_RING * (gm.NW + 1) * 1024 + (size_t)4 * 1024 + (size_t)gm.NW * (pair ? 2 : IROW_NS) * gm.sb +
+           ((size_t)4 * gm.Ds + nj + nk + 32 + 2 * (gm.NW + 1) * IROW_RING + gm.NW * IROW_NS + 2) * sizeof(double);
+    if (smem <= 226 * 1024 || !pair) break;
+    pair = false;
+  }
   const int ER = 32 / LR;
   const int ngroups = (gm.Ds * gm.Gs + ER - 1) / ER;
   gm.ngroups = ngroups;
@@ -554,12 +617,15 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
   if (pp && (long long)cps * n > pop_capacity) pp = nullptr;
   if (pop_count) *pop_count = pp ? cps * n : 0;
   const kb200_sweep_desc *dd = (const kb200_sweep_desc *)d_descs;
+#define IROW_LAUNCH(LR_) return pair ? launch_irow<LR_, true>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st) \
+                                    : launch_irow<LR_, false>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st)
   switch (LR) {
-    case 1: return launch_irow<1>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st);
-    case 2: return launch_irow<2>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st);
-    case 4: return launch_irow<4>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st);
-    case 8: return launch_irow<8>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st);
-    case 16: return launch_irow<16>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st);
-    default: return launch_irow<32>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st);
+    case 1: IROW_LAUNCH(1);
+    case 2: IROW_LAUNCH(2);
+    case 4: IROW_LAUNCH(4);
+    case 8: IROW_LAUNCH(8);
+    case 16: IROW_LAUNCH(16);
+    default: IROW_LAUNCH(32);
   }
+#undef IROW_LAUNCH
 }
