@@ -49,6 +49,7 @@ struct IGeom {  // kernel parameter: lives in the constant bank, costs no regist
   int NW, nkt;  // warps (= k-planes) per CTA, k tiles
   int E, ngroups;
   unsigned sb, vol_off;  // bytes of one staging slot and offset of the zone-volume rows in it
+  int sig1;              // the ER rows of a warp always share their group (Ds % ER == 0): one sigt row (pair) per step
   unsigned sa, sg, Zs, ipd, ipg, jpd, jpg, kpd, kpg;  // element strides: psi/rhs (direction, group), zones, planes
 };
 
@@ -224,13 +225,14 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
     const bool kload = (w == 0) && !(k_zero && ktile0);
     if (w == 0 && !ktile0) ir_wait_ge(sh.prod, qn + 2u - (unsigned)nj);
     const unsigned bar = sbar0 + 8u * sqn;
-    if (lane == 0) ir_mb_expect_tx(bar, (kload ? 3u : 2u) * 2u * rowb * (unsigned)(32 / LR) + (POP ? 2u * rowb : 0u));
+    if (lane == 0)
+      ir_mb_expect_tx(bar, (kload ? 2u : 1u) * 2u * rowb * (unsigned)(32 / LR) + 2u * rowb * (gm.sig1 ? 1u : (unsigned)(32 / LR)) + (POP ? 2u * rowb : 0u));
     __syncwarp();  // also: every lane is done reading the slot's previous contents
     if (ls == 0) {
       const unsigned roff = (unsigned)(((jd > 0) ? 2 * pp : 2 * pp + 1) * jstep);  // the lower of the two rows in memory
       const unsigned dst = stage0 + sqn * SB + (unsigned)seg * 2u * rowb;
       ir_bulk_g2s(dst, ds.rhs + (it.off0 + roff), 2u * rowb, bar);
-      ir_bulk_g2s(dst + RB, ds.sigt + (it.soff0 + roff), 2u * rowb, bar);
+      if (!gm.sig1 || lane == 0) ir_bulk_g2s(dst + RB, ds.sigt + (it.soff0 + roff), 2u * rowb, bar);
       if (kload) ir_bulk_g2s(kin0 + sqn * RB + (unsigned)seg * 2u * rowb, ds.k_plane + (it.kpx0 + roff), 2u * rowb, bar);
       if (POP && lane == 0) ir_bulk_g2s(stage0 + sqn * SB + gm.vol_off, vol + (it.soff0 - (unsigned)it.g * gm.Zs + roff), 2u * rowb, bar);
     }
@@ -316,7 +318,8 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
       double A[4], rc[4], r4[4];
       const double cy = tyc * sh.rdy[jz];
       {
-        const double2 e = ir_lds128(st + RB), f = ir_lds128(st + RB + 16);
+        const unsigned sgo = (PAIR && gm.sig1) ? st - (unsigned)seg * 2u * rowb : st;  // shared rows: segment 0's block
+        const double2 e = ir_lds128(sgo + RB), f = ir_lds128(sgo + RB + 16);
         const double s4[4] = {e.x, e.y, f.x, f.y};
         const double2 a = ir_lds128(st), b = ir_lds128(st + 16);
         r4[0] = a.x; r4[1] = a.y; r4[2] = b.x; r4[3] = b.y;
@@ -590,6 +593,7 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
   // k faces of a row the last warp can only produce after warp 0 has moved on
   if (nj <= IROW_PD) return -1;
   // staging layout: row pairs (two slots) when nj is even and it fits, single rows (three slots) otherwise
+  gm.sig1 = (gm.Ds % (32 / LR) == 0) ? 1 : 0;
   const unsigned rowb = 8u * (unsigned)ni;
   const char *pe = getenv("KB200_IROW_PAIR");
   bool pair = (nj % 2 == 0) && nj >= 4 && !(pe && pe[0] == '0');
