@@ -183,8 +183,10 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
   const unsigned kin0 = sh.kin;                                             // + slot * RB (warp 0): k_plane rows of the ER segments
   const unsigned sbar0 = sh.sbar + 8u * (unsigned)(w * NS);                 // + 8 * slot
   const unsigned mine = (unsigned)seg * (PAIR ? 2u : 1u) * rowb + 8u * i0;   // this lane's four zones inside a staged row block
-  const unsigned fk_in0 = sh.fkx + (unsigned)w * 1024u + 16u * lane;                       // + ring slot * (NW+1)*1024
-  const unsigned fkx_slot = (unsigned)(NW + 1) * 1024u;
+  // k-face ring: one row per slot, or (PAIR) the two rows of a pair per slot and hand-shake
+  constexpr unsigned RINGB = PAIR ? 2048u : 1024u;
+  const unsigned fk_in0 = sh.fkx + (unsigned)w * RINGB + 16u * lane;        // + ring slot * (NW+1)*RINGB (+ 1024 for the pair's second row)
+  const unsigned fkx_slot = (unsigned)(NW + 1) * RINGB;
   const unsigned full_in = sh.full + 8u * (unsigned)(w * R), full_out = full_in + 8u * R;
   const unsigned empty_in = sh.empty + 8u * (unsigned)(w * R), empty_out = empty_in + 8u * R;
 
@@ -260,13 +262,13 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
     const bool nx_pre = nx_ok && nx.kv;
 
     if (!it.kv) {  // this warp's plane does not exist in the (short) last k tile: only keep the ring handshakes going
-      for (int j = 0; j < nj; ++j) {
+      for (int j = 0; j < nj; j += (PAIR ? 2 : 1)) {
         if (w > 0) { ir_mb_wait(full_in + 8u * slot, ph); ir_mb_arrive(empty_in + 8u * slot); }
         if (w < NW - 1) {
-          if (q >= (unsigned)R) ir_mb_wait(empty_out + 8u * slot, ph ^ 1u);
+          if (q >= (unsigned)(PAIR ? 2 * R : R)) ir_mb_wait(empty_out + 8u * slot, ph ^ 1u);
           ir_mb_arrive(full_out + 8u * slot);
         }
-        ++q;
+        q += PAIR ? 2u : 1u;
         if (++slot == R) { slot = 0; ph ^= 1u; }
       }
       if (PAIR) {  // the next item (tile 0 of the next group) starts from scratch
@@ -352,11 +354,11 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
       double fk[4];
       {
         if (w > 0) {
-          ir_mb_wait(full_in + 8u * slot, ph);
-          const unsigned src = fk_in0 + slot * fkx_slot;
+          if (!PAIR || PAR == 0) ir_mb_wait(full_in + 8u * slot, ph);
+          const unsigned src = fk_in0 + slot * fkx_slot + ((PAIR && PAR == 1) ? 1024u : 0u);
           const double2 k0 = ir_lds128(src), k1 = ir_lds128(src + 512);
           fk[0] = k0.x; fk[1] = k0.y; fk[2] = k1.x; fk[3] = k1.y;
-          ir_mb_arrive(empty_in + 8u * slot);  // the slot may be refilled
+          if (!PAIR || PAR == 1) ir_mb_arrive(empty_in + 8u * slot);  // the slot may be refilled
         } else if (k_zero && ktile0) {
           fk[0] = fk[1] = fk[2] = fk[3] = 0.0;
         } else {
@@ -406,11 +408,11 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
         ok[m] = fma(2.0, p, -fk[m]);
       }
       if (w < NW - 1) {  // (the last plane of a short tile publishes too: idle warps keep shaking hands)
-        if (q >= (unsigned)R) ir_mb_wait(empty_out + 8u * slot, ph ^ 1u);  // warp w+1 has emptied this ring slot
-        const unsigned dst = fk_in0 + slot * fkx_slot + 1024u;
+        if ((!PAIR || PAR == 0) && q >= (unsigned)(PAIR ? 2 * R : R)) ir_mb_wait(empty_out + 8u * slot, ph ^ 1u);  // warp w+1 has emptied this ring slot
+        const unsigned dst = fk_in0 + slot * fkx_slot + RINGB + ((PAIR && PAR == 1) ? 1024u : 0u);
         ir_sts128(dst, ok[0], ok[1]);
         ir_sts128(dst + 512, ok[2], ok[3]);
-        ir_mb_arrive(full_out + 8u * slot);
+        if (!PAIR || PAR == 1) ir_mb_arrive(full_out + 8u * slot);
       }
       if (it.ev) {
         ir_stg256(ds.psi + (off + i0), p4);
@@ -446,7 +448,9 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
       } else {
         if (++sq == (unsigned)NS) { sq = 0; sph ^= 1u; }
       }
-      if (++slot == R) { slot = 0; ph ^= 1u; }
+      if (!PAIR || PAR == 1) {
+        if (++slot == R) { slot = 0; ph ^= 1u; }
+      }
       off += (unsigned)jstep; ipx += (unsigned)jd; jz += jd;
     };
     if (PAIR) {
@@ -478,7 +482,7 @@ __global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sw
   const int Ds = gm.Ds, nj = gm.nj, nk = gm.nk, NW = gm.NW;
   IShared sh;
   unsigned char *p = ism;
-  sh.fkx = ir_smem_addr(p); p += (size_t)IROW_RING * (NW + 1) * 1024;
+  sh.fkx = ir_smem_addr(p); p += (size_t)IROW_RING * (NW + 1) * (PAIR ? 2048 : 1024);
   sh.kin = ir_smem_addr(p); p += (size_t)4 * 1024;
   sh.stage = ir_smem_addr(p); p += (size_t)NW * (PAIR ? 2 : IROW_NS) * gm.sb;
   double *tab = reinterpret_cast<double *>(p);
@@ -600,9 +604,9 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
   size_t smem = 0;
   for (;;) {
     const unsigned rb = pair ? 2048u : 1024u;
-    gm.vol_off = 2u * rb;
+    gm.vol_off = rb + ((pair && gm.sig1) ? 2u * rowb : rb);  // a shared sigt row pair takes 2*rowb instead of a full block
     gm.sb = gm.vol_off + (d_pop_partial ? (pair ? 2u : 1u) * rowb : 0u);
-    smem = (size_t)IROW_RING * (gm.NW + 1) * 1024 + (size_t)4 * 1024 + (size_t)gm.NW * (pair ? 2 : IROW_NS) * gm.sb +
+    smem = (size_t)IROW_RING * (gm.NW + 1) * rb + (size_t)4 * 1024 + (size_t)gm.NW * (pair ? 2 : IROW_NS) * gm.sb +
            ((size_t)4 * gm.Ds + nj + nk + 32 + 2 * (gm.NW + 1) * IROW_RING + gm.NW * IROW_NS + 2) * sizeof(double);
     if (smem <= 226 * 1024 || !pair) break;
     pair = false;
