@@ -11,8 +11,11 @@
  *  - every function returns 0 on success, otherwise a non-zero code; kb200_last_error() gives the
  *    message (thread-local).  The C++ wrapper turns non-zero into KRIPKE_ABORT semantics.
  *  - all pointers named d_* / inside descriptors are DEVICE pointers of the current device,
- *    h_* are host pointers.  No function allocates behind the caller's back except kb200_alloc
- *    and the plan objects.
+ *    h_* are host pointers.  Fields are never allocated behind the caller's back; the library keeps
+ *    a few private scratch buffers that live until kb200_finalize: the device copies of the
+ *    descriptors, the per-zone material fractions of kb200_scattering, and -- only for the
+ *    nestings whose moments are not zone-fastest -- two transposed copies of a moments chunk.
+ *    kb200_free keeps blocks up to 64 MB in a pool for the next kb200_alloc of the same size.
  *  - `layout` is the reference's LayoutV value: 0=DGZ 1=DZG 2=GDZ 3=GZD 4=ZDG 5=ZGD
  *    (src/Kripke/ArchLayout.h:92-101); storage orders follow src/Kripke/VarTypes.h:73-101.
  *  - `stream` is a cudaStream_t passed as void* (NULL = the library's default stream).

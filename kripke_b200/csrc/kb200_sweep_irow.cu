@@ -22,9 +22,12 @@
 //     warp waits for its upwind k faces; then each lane composes its four zone maps, a
 //     Kogge-Stone scan over the LR lanes (log2(LR) steps of 64-bit shuffles) gives every lane its
 //     incoming i-face flux, and the four zones are finished locally;
-//   * everything a row needs from global memory (rhs, sigt, incoming i face, tile-boundary k
-//     faces) is brought in IROW_PD row steps ahead by cp.async into a per-warp staging ring
-//     (each lane reads back only what it copied itself: no barrier, no registers held by loads).
+//   * everything a row needs from global memory (rhs rows, sigt rows, tile-boundary k faces, zone
+//     volumes for the fused population sum) is brought in ahead of time by TMA bulk copies
+//     (cp.async.bulk, completion counted in bytes on a per-slot mbarrier) into a per-warp staging
+//     ring: no registers held by loads, and none of the per-lane cp.async (LDGSTS) traffic that
+//     saturated first.  Rows j and j+1 of a k-plane are adjacent in memory, so with an even nj one
+//     copy per array brings in a row PAIR and the k-face ring is handed over once per pair.
 // The scan re-associates the i recurrence and 2*cos/delta is formed as (2*cos)*(1/delta), so
 // results differ from the reference in the last bits (|difference| ~ 1e-16 relative; contractions
 // |2A-1| < 1 keep the recurrence stable).  EXACT mode and shapes this kernel does not cover use
@@ -40,9 +43,8 @@ constexpr int IROW_RING = 2;   // slots of the k-face ring between neighbouring 
 constexpr int IROW_PD = 2;     // prefetch distance in row steps
 constexpr int IROW_NS = IROW_PD + 1;  // staging slots per warp
 constexpr int IROW_MAXW = 16, IROW_MAXT = IROW_MAXW * 32;  // warps per CTA: up to 128 registers per thread (22 warps x 80 registers spill)
-// per warp and staging slot: the rhs rows and the sigt rows of the warp's ER elements in memory order (1 KB each)
-// (+ one row of zone volumes, shared by the ER segments, when the population sum is fused in)
-constexpr int IROW_STAGE_BYTES = 1024 + 1024, IROW_STAGE_BYTES_POP = IROW_STAGE_BYTES + 1024;
+// per warp and staging slot: the rhs rows and the sigt rows of the warp's ER elements in memory order (1 KB each per
+// row of the slot) + one row of zone volumes per row of the slot when the population sum is fused in: IGeom::sb
 
 struct IGeom {  // kernel parameter: lives in the constant bank, costs no registers
   int layout, Ds, Gs, ni, nj, nk;
@@ -53,10 +55,6 @@ struct IGeom {  // kernel parameter: lives in the constant bank, costs no regist
   unsigned sa, sg, Zs, ipd, ipg, jpd, jpg, kpd, kpg;  // element strides: psi/rhs (direction, group), zones, planes
 };
 
-__device__ __forceinline__ void ir_ldg256_nc(const double *p, double (&v)[4]) {
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-               : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-}
 __device__ __forceinline__ void ir_ldg256_cg(const double *p, double (&v)[4]) {
   asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
 }
@@ -64,23 +62,9 @@ __device__ __forceinline__ void ir_stg256(double *p, const double (&v)[4]) {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
 __device__ __forceinline__ unsigned ir_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ir_cp_async16(unsigned smem_dst, const void *gsrc, int src_size) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_size) : "memory");
-}
-__device__ __forceinline__ void ir_cp_async8(unsigned smem_dst, const void *gsrc, int src_size) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_size) : "memory");
-}
-__device__ __forceinline__ void ir_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void ir_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ double2 ir_lds128(unsigned addr) {
   double2 v;
   asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ double ir_lds64(unsigned addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
   return v;
 }
 __device__ __forceinline__ void ir_sts128(unsigned addr, double x, double y) {
@@ -122,7 +106,7 @@ __device__ __forceinline__ void ir_mb_wait(unsigned addr, unsigned parity) {  //
 struct IShared {  // shared-window addresses of the pieces of dynamic shared memory
   unsigned fkx;          // [IROW_RING][NW+1][2][32] double2: k-face exchange ring (entry 0 of a slot row is unused)
   unsigned kin;          // [IROW_NS][2][32] double2: warp 0's tile-boundary k faces
-  unsigned stage;        // [NW][IROW_NS] staging slots of IROW_STAGE_BYTES
+  unsigned stage;        // [NW][2 or IROW_NS] staging slots of IGeom::sb bytes
   unsigned full, empty;  // [NW+1][IROW_RING] mbarriers of the ring slots (32 arrivals each)
   unsigned sbar;         // [NW][IROW_NS] mbarriers of the staging slots (1 arrival + the bytes of the bulk copies)
   unsigned prod;         // [1] rows whose tile-boundary k faces the last warp has put into k_plane
