@@ -346,3 +346,29 @@ def test_moments_tensor_core_packed_zdg(gpu, legendre, quad):
     assert_close(p.field("rhs"), o.field("rhs"), "LPlusTimes packed ZDG", False)
     o.ltimes(); p.call("LTimes")  # accumulate on top
     assert_close(p.field("phi"), o.field("phi"), "LTimes accumulate packed ZDG", False)
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("layout", ["DGZ", "GZD", "ZGD", "DZG"])
+def test_sweep_with_non_uniform_mesh(gpu, layout, exact):
+    """the generated mesh is uniform, which would hide a wrong 2*cos/delta per zone: stretch dx, dy, dz on both
+    sides (SweepSubdomain.cpp:88-93 divides by the width of each zone) and sweep with non-zero inflow."""
+    gpu.abi().kb200_set_exact(int(exact))
+    try:
+        args = f"--zones 16,10,12 --groups 4 --quad 16 --legendre 1 --gset 1 --dset 8 --zset 1,1,1 --layout {layout}"
+        p, o, _, _ = pair(gpu, args)
+        for name, seed in (("dx", 7100), ("dy", 7200), ("dz", 7300)):
+            for c in range(o.num_chunks(name)):
+                v = o.chunk(name, c) * seeded(len(o.chunk(name, c)), seed + c, 0.5, 1.5)
+                o.chunk(name, c)[:] = v
+                p.set_chunk(name, c, v)
+        fill_both(p, o, "rhs", 7400, 0.0, 1.0)
+        for f, s in (("i_plane", 7500), ("j_plane", 7600), ("k_plane", 7700)):
+            fill_both(p, o, f, s, 0.0, 0.5)
+        for sdom in range(o.num_subdomains()):
+            o.sweep_subdomain(sdom)
+            p.call(f"sweepSubdomain:{sdom}")
+        for f in ("psi", "i_plane", "j_plane", "k_plane"):
+            assert_close(p.field(f), o.field(f), f"non-uniform mesh {f} {layout}", exact)
+    finally:
+        gpu.abi().kb200_set_exact(0)
