@@ -76,10 +76,11 @@ MOMENT_SHAPES = [
     # (legendre, quad): M = 25 exercises the 3-tile + DFMA-row LTimes and the K = 4*6+1 LPlusTimes paths of
     # kb200_moments_mma.cu; M = 100 the wide-output / streamed-K paths; M = 1 the degenerate one
     (4, 96), (9, 16), (0, 8), (5, 40),
+    (4, 192),  # BASELINE config 2's shape per direction set (Ds = 24, M = 25): 16-byte fragment loads + the DFMA column/row
 ]
 
 
-@pytest.mark.parametrize("layout", ["DGZ", "DZG", "GDZ"])
+@pytest.mark.parametrize("layout", ["DGZ", "DZG", "GDZ", "GZD", "ZGD"])  # kb200_moments_mma.cu / kb200_moments_rowmma.cu
 @pytest.mark.parametrize("shape", range(len(MOMENT_SHAPES)))
 def test_moments_tensor_core_shapes(gpu, shape, layout):
     L, quad = MOMENT_SHAPES[shape]
