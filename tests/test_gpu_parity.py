@@ -373,3 +373,18 @@ def test_sweep_with_non_uniform_mesh(gpu, layout, exact):
             assert_close(p.field(f), o.field(f), f"non-uniform mesh {f} {layout}", exact)
     finally:
         gpu.abi().kb200_set_exact(0)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_scattering_at_config2_group_structure(gpu, layout):
+    """two source group sets of 32 groups, M = 25 (the 4-tile CTAs of kb200_scatter_mma.cu and, for the nestings whose
+    zone index is not fastest, the transposes around it), dense asymmetric sigs, mixed-material zones, then '+='."""
+    args = f"--zones 12,8,10 --groups 64 --quad 8 --legendre 4 --gset 2 --dset 8 --zset 1,2,1 --layout {layout}"
+    p, o, _, _ = pair(gpu, args)
+    fill_both(p, o, "data/sigs", 8100, 0.0, 0.1)
+    fill_both(p, o, "phi", 8200, -1.0, 1.0)
+    o.zero("phi_out"); o.scattering(); o.source()
+    p.call("zero:phi_out"); p.call("scattering"); p.call("source")
+    assert_close(p.field("phi_out"), o.field("phi_out"), f"scattering {layout}", False)
+    o.scattering(); p.call("scattering")  # accumulate on top of the previous result
+    assert_close(p.field("phi_out"), o.field("phi_out"), f"scattering accumulate {layout}", False)
