@@ -162,14 +162,20 @@ __global__ void __launch_bounds__(kPopThreads) population_vec_kernel(const kb200
   const unsigned items_per_desc = (unsigned)n0 * segs;
   const unsigned long long nitems = (unsigned long long)items_per_desc * ndesc;
   double local = 0.0;
-  for (unsigned long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+  // zone-slowest orders have only Gs*Ds elements per slowest index: a whole block per item would idle most threads
+  // and pay the item decode per 6 KB, so there a WARP owns an item
+  const bool warp_items = inner <= 2048u;
+  const unsigned tid = warp_items ? (threadIdx.x & 31u) : threadIdx.x, nthr = warp_items ? 32u : (unsigned)kPopThreads;
+  const unsigned long long first = warp_items ? (unsigned long long)blockIdx.x * (kPopThreads / 32) + (threadIdx.x >> 5) : blockIdx.x;
+  const unsigned long long stride = warp_items ? (unsigned long long)gridDim.x * (kPopThreads / 32) : gridDim.x;
+  for (unsigned long long item = first; item < nitems; item += stride) {
     const unsigned di = (unsigned)(item / items_per_desc);
     const unsigned rem = (unsigned)(item - (unsigned long long)di * items_per_desc);
     const unsigned i0 = rem / segs, seg = rem - i0 * segs;
     const kb200_population_desc &ds = descs[di];
     const double *__restrict__ psi = ds.psi + (size_t)i0 * inner;
     const unsigned lo = seg * kPopVecSeg, hi = min(inner, lo + kPopVecSeg);
-    for (unsigned j = lo + 4 * threadIdx.x; j < hi; j += 4 * kPopThreads) {
+    for (unsigned j = lo + 4 * tid; j < hi; j += 4 * nthr) {
       const unsigned q = j / (unsigned)n2, r = j - q * (unsigned)n2;
       double v[4];
       asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
