@@ -89,11 +89,13 @@ int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_d
 int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, cudaStream_t st) {
   const int layout = h[0].layout;
   if (layout != 1 && layout != 3 && layout != 4 && layout != 5) return -1;
-  // group-fastest nestings (DZG, ZDG) go through the generic layout transform, which cannot fold a "+="
-  const bool generic = (layout == 1 || layout == 4);
-  if (generic)
-    for (int i = 0; i < n; ++i)
-      if (h[i].accumulate) return -1;
+  // The tiled generic layout transform is the faster transposer (measured 5.2 against 5.9-7.1 ms per scattering call)
+  // but cannot fold a "+=": the moment-fastest nestings keep their own kernel for that case, the group-fastest ones
+  // (DZG, ZDG) fall back to the DFMA kernel.
+  bool any_acc = false;
+  for (int i = 0; i < n; ++i) any_acc |= (h[i].accumulate != 0);
+  if (any_acc && (layout == 1 || layout == 4)) return -1;
+  const bool generic = !any_acc;
   const char *env = getenv("KB200_SCATTER_DFMA");
   if (env && env[0] == '1') return -1;
   const int M = h[0].M, Gs = h[0].Gs, Zs = h[0].Zs;
