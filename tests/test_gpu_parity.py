@@ -388,3 +388,27 @@ def test_scattering_at_config2_group_structure(gpu, layout):
     assert_close(p.field("phi_out"), o.field("phi_out"), f"scattering {layout}", False)
     o.scattering(); p.call("scattering")  # accumulate on top of the previous result
     assert_close(p.field("phi_out"), o.field("phi_out"), f"scattering accumulate {layout}", False)
+
+
+def test_kripke_exe_command_line_and_output(gpu, goldens):
+    """the drop-in executable: the reference's command line in, the reference's iteration lines, TIMER_NAMES/TIMER_DATA
+    and figures of merit out (src/kripke.cpp:480-516, SteadyStateSolver.cpp:86-90, Timing.cpp:78-95)."""
+    import os
+    import re
+    import subprocess
+    from conftest import ROOT
+    g = goldens["G1_default"]
+    exe = os.path.join(ROOT, "kripke_b200", "bin", "kripke.exe")
+    out = subprocess.run([exe] + g["args"].split(), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    parts = [float(m) for m in re.findall(r"iter \d+: particle count=([0-9.e+-]+)", out.stdout)]
+    assert len(parts) == len(g["particles"])
+    for a, b in zip(parts, g["particles"]):
+        assert abs(a - b) <= 1e-6 * abs(b)  # printed with %e like the reference
+    names = re.search(r"TIMER_NAMES:(.*)", out.stdout).group(1).split(",")
+    data = re.search(r"TIMER_DATA:(.*)", out.stdout).group(1).split(",")
+    assert len(names) == len(data) and {"Solve", "LTimes", "LPlusTimes", "Scattering", "Source", "SweepSolver", "SweepSubdomain",
+                                         "Population", "Generate"} <= {n.strip() for n in names}
+    assert all(float(x) >= 0.0 for x in data)
+    assert "Figures of Merit" in out.stdout and "Grind time" in out.stdout and "Number of unknowns: 12582912" in out.stdout
+    assert out.stdout.rstrip().endswith("END")
