@@ -90,14 +90,51 @@ def measured_peaks():
 
 
 def ncu_traffic(workload, layout, kernel):
-    """DRAM bytes (read + write) per launch of the entry point's kernel, from the committed ncu --set full capture
-    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py); None if that capture does not exist."""
+    """DRAM bytes (read + write) per launch of the entry point's kernel from the committed `ncu --set full` capture of the
+    same workload (profiles/ncu_traffic.json, written by tools/ncu_traffic.py), and where that number comes from: the
+    capture file and the commit it was taken at.  (None, None) if no capture of this workload/layout exists -- a number
+    measured under a profiler cannot be produced inside a timing run."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(path) as f:
-            return json.load(f)[f"{workload}:{layout}"]["per_entry_point"][kernel]["dram_bytes_per_launch"]
+            e = json.load(f)[f"{workload}:{layout}"]
+        return e["per_entry_point"][kernel]["dram_bytes_per_launch"], {"file": "profiles/ncu_traffic.json", "capture": e.get("source"),
+                                                                      "commit": e.get("commit")}
     except Exception:
-        return None
+        return None, None
+
+
+def host_mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def reference_sample_zones(workload, steps, warmup, budget_s=240.0):
+    """The zone block the reference arm runs: the workload's own per-GPU block if the host can hold it (fields take
+    ~18.5 bytes x unknowns plus moments) and steps+warmup iterations fit the time budget at the CPU rate measured by
+    earlier runs (~5.4 ns per unknown and iteration on 16 threads), else the largest halving of it that does."""
+    zones, groups, dirs, leg, _ = WORKLOADS[workload]
+    M = (leg + 1) ** 2
+    cores = os.cpu_count() or 1
+    rate = 5.4e-9 * 16.0 / max(cores, 1)
+    mem = host_mem_available_gb() * 1e9
+    z = list(zones)
+    k = 2
+    while True:
+        nz = z[0] * z[1] * z[2]
+        bytes_needed = nz * groups * (16.0 * dirs + 16.0 * M + 8.0) * 1.15
+        secs = nz * groups * dirs * rate * (steps + warmup)
+        if (bytes_needed <= 0.8 * mem and secs <= budget_s) or nz <= 16 ** 3:
+            return tuple(z)
+        if z[k] > 8:
+            z[k] //= 2
+        k = (k - 1) % 3
 
 
 def run_reference_cpu(workload, layout, steps, warmup, zones):
@@ -112,6 +149,7 @@ def run_reference_cpu(workload, layout, steps, warmup, zones):
     cmd = [ref, "--arch", "OpenMP", "--layout", layout, "--zones", "%d,%d,%d" % zones, "--groups", str(groups),
            "--quad", str(dirs), "--legendre", str(leg), "--niter", str(steps + warmup), "--time"] + extra.split()
     out = subprocess.check_output(cmd, text=True, env=env)
+    command = "kripke " + " ".join(cmd[1:])
     times = [float(l.split()[2]) for l in out.splitlines() if l.startswith("ITER_TIME")]
     timers = {l.split()[1]: float(l.split()[2]) for l in out.splitlines() if l.startswith("TIMER ")}
     unknowns = groups * dirs * zones[0] * zones[1] * zones[2]
@@ -119,7 +157,7 @@ def run_reference_cpu(workload, layout, steps, warmup, zones):
     return {"value": 1e9 * t / unknowns, "unit": "ns/(unknown*iter)", "cores": cores, "kind": "reference",
             "sample": f"unmodified reference (OpenMP, {cores} threads), zones {zones[0]}x{zones[1]}x{zones[2]} of the "
                       f"workload's {groups} groups x {dirs} directions, {len(times[warmup:])} timed iterations after {warmup} warm-up",
-            "s_per_iter": t, "unknowns": unknowns, "kernel_seconds_total": timers}
+            "s_per_iter": t, "unknowns": unknowns, "kernel_seconds_total": timers, "command": command, "zones": list(zones)}
 
 
 def main():
@@ -131,7 +169,8 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--layout", default=os.environ.get("KB200_BENCH_LAYOUT", "DGZ"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-zones", default="32,32,32", help="zones of the CPU sample for --impl reference")
+    ap.add_argument("--ref-zones", default="auto", help="zones of the CPU sample for --impl reference (auto: the largest "
+                    "halving of the workload's block that fits host memory and a few minutes)")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -142,16 +181,20 @@ def main():
         sys.exit(f"--gpus {n_gpus} but WORLD_SIZE={world}")
 
     kargs, unknowns = kripke_args(args.workload, n_gpus, args.layout, args.steps + warmup)
-    config = {"workload": f"Kobayashi-3i synthetic, BASELINE {args.workload}: {' '.join(kargs)} "
-                          f"({WORKLOADS[args.workload][0][0]}^3 zones per GPU)",
-              "layout": args.layout, "unknowns": unknowns, "l2_policy": "inputs larger than L2 (59.5 GB of fields per GPU)",
+    wz, wg, wd, wl, wx = WORKLOADS[args.workload]
+    # the named workload; the command line each arm actually ran is the line's own "command" key
+    config = {"workload": f"Kobayashi-3i synthetic, BASELINE {args.workload}: {wz[0]}x{wz[1]}x{wz[2]} zones per GPU, {wg} groups, "
+                          f"{wd} directions, legendre {wl}{(' ' + wx) if wx else ''}, one source iteration per step",
+              "layout": args.layout, "unknowns": unknowns,
+              "l2_policy": "inputs larger than L2 (%.1f GB of fields per GPU)" % (unknowns / n_gpus * (16.0 + 16.0 * (wl + 1) ** 2 / wd) / 1e9),
               "parallelism": f"kba{n_gpus}" if n_gpus > 1 else "single"}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return
-        zones = tuple(int(x) for x in args.ref_zones.split(","))
+        zones = reference_sample_zones(args.workload, args.steps, warmup) if args.ref_zones == "auto" \
+            else tuple(int(x) for x in args.ref_zones.split(","))
         r = run_reference_cpu(args.workload, args.layout, args.steps, warmup, zones)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/kripke_ref was not built"}))
@@ -162,6 +205,9 @@ def main():
                 "throughput_unknowns_per_s": 1e9 / r["value"],
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "command": r["command"], "sample_zones": r["zones"], "sample_unknowns": r["unknowns"],
+                "sample_is_full_workload": list(r["zones"]) == list(WORKLOADS[args.workload][0]) and n_gpus == 1,
+                "host_mem_available_gb": host_mem_available_gb(),
                 "kernel_seconds_total": r["kernel_seconds_total"]}
         print(json.dumps(line))
         return
@@ -194,6 +240,40 @@ def main():
             dist.barrier()
 
     H.kripke_b200_timer_sync(0)
+
+    # ---- parity of the multi-GPU path on THIS box, before anything is timed (N > 1): the KBA sweep and the block-Jacobi
+    # exchange over NCCL must reproduce the particle counts of the unmodified reference for the equivalent single-rank
+    # zone-set decomposition (--procs px,py,pz --zset a,b,c == one rank with --zset px*a,py*b,pz*c)
+    parity = None
+    if world > 1:
+        with open(os.path.join(ROOT, "tests", "golden", "reference_goldens.json")) as f:
+            gold = json.load(f)
+        px, py, pz = PROCS[n_gpus]
+        parity = {"rtol": 1e-12, "cases": {}, "max_rel_err": 0.0}
+        for name in ("G4_kba_proxy", "G5_block_jacobi", "L_GZD", "L_ZGD"):
+            a = gold[name]["args"].split()
+            zs = [1, 1, 1]
+            if "--zset" in a:
+                i = a.index("--zset")
+                zs = [int(x) for x in a[i + 1].split(",")]
+                del a[i:i + 2]
+            if zs[0] % px or zs[1] % py or zs[2] % pz:
+                continue
+            a += ["--zset", "%d,%d,%d" % (zs[0] // px, zs[1] // py, zs[2] // pz), "--procs", "%d,%d,%d" % (px, py, pz)]
+            q = kb.Problem(a)
+            got = q.solve()
+            q.close()
+            ref = gold[name]["particles"]
+            err = max(abs(x - y) / abs(y) for x, y in zip(got, ref)) if len(got) == len(ref) else float("inf")
+            parity["cases"][name] = {"args": " ".join(a), "max_rel_err": err}
+            parity["max_rel_err"] = max(parity["max_rel_err"], err)
+            dist.barrier()
+        parity["case"] = ",".join(parity["cases"])
+        if not parity["cases"] or parity["max_rel_err"] > parity["rtol"]:
+            if rank == 0:
+                print(json.dumps({"error": "multi-GPU parity check failed, nothing was timed", "parity": parity}))
+            sys.exit(3)
+
     p = kb.Problem(kargs)
 
     # e2e staging: every generated input table of the step lives in pinned host memory and is
@@ -219,6 +299,8 @@ def main():
             A.kb200_upload(p.device_ptr(name, c, True), hp, nbytes, None)
 
     kernels = ["LTimes", "scattering", "source", "LPlusTimes", "SweepSolver", "population"]
+    A.kb200_last_sweep_kernel.restype = C.c_char_p
+    sweep_kernels = set()
     ev = {}
     for k in kernels:
         a, b = C.c_void_p(), C.c_void_p()
@@ -241,6 +323,8 @@ def main():
             r = p.call(k)
             if timed:
                 A.kb200_event_record(ev[k][1], None)
+            if k == "SweepSolver":
+                sweep_kernels.add(A.kb200_last_sweep_kernel().decode())
             if k == "population":
                 particles.append(r)  # 8-byte device->host read of the step's result
         if timed:
@@ -298,9 +382,18 @@ def main():
                "SweepSolver": 16 * N_u, "population": 8 * N_u, "source": 0.0}
         flops = {"LTimes": 2 * M * N_u, "LPlusTimes": 2 * M * N_u, "scattering": 2 * G * N_m}
         peak, peak_src = measured_peaks()
+        pop_fused = any("+population" in x for x in sweep_kernels)
         per_kernel = {}
         for k in kernels:
             ms_k = statistics.mean(ktime[k]) if ktime[k] else None
+            if k == "population" and pop_fused:
+                # the sum was accumulated by the sweep kernel while psi was in registers: this entry point only adds up the
+                # per-CTA partials and reads 8 bytes back -- it moves no algorithmic bytes of its own
+                per_kernel[k] = {"ms": ms_k, "fused": True, "fused_into": "SweepSolver", "alg_GBs_per_gpu": None, "frac_of_hbm_peak": None}
+                continue
+            if k == "source":
+                per_kernel[k] = {"ms": ms_k, "alg_GBs_per_gpu": None, "frac_of_hbm_peak": None}
+                continue
             per_kernel[k] = {"ms": ms_k, "alg_GBs_per_gpu": (alg[k] / n_gpus / (ms_k * 1e-3) / 1e9) if ms_k else None,
                              "frac_of_hbm_peak": (alg[k] / n_gpus / (ms_k * 1e-3) / 1e9 / peak) if ms_k else None}
             if k in flops and ms_k:
@@ -308,6 +401,7 @@ def main():
         dom = max(kernels, key=lambda k: per_kernel[k]["ms"] or 0)
         grind_ns = 1e9 * dev_s / args.steps / unknowns
         e2e_ns = 1e9 * e2e_s / args.steps / unknowns
+        traffic, traffic_src = ncu_traffic(args.workload, args.layout, dom) if n_gpus == 1 else (None, None)
         line = {"metric": "grind_time", "value": grind_ns, "unit": "ns/(unknown*iter)", "n_gpus": n_gpus,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": False,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -317,10 +411,12 @@ def main():
                         "what": "source iteration through the C++ Kripke:: host layer; all generated input tables "
                                 "re-uploaded from pinned host memory and the particle count read back every step"},
                 "gpu_launches": int(launches.value),
+                "command": "kripke " + " ".join(kargs),
+                "sweep_kernel": "|".join(sorted(sweep_kernels)),
                 "clocks": clocks,
                 "roofline": {"kernel": dom, "bound": "hbm", "achieved": per_kernel[dom]["alg_GBs_per_gpu"], "peak": peak,
                              "unit": "GB/s", "frac": per_kernel[dom]["frac_of_hbm_peak"],
-                             "traffic": ncu_traffic(args.workload, args.layout, dom) if n_gpus == 1 else None,
+                             "traffic": traffic, "traffic_source": traffic_src,
                              "algorithmic_bytes": alg[dom] / n_gpus,
                              "peak_source": peak_src},
                 "per_kernel": per_kernel,
@@ -328,11 +424,13 @@ def main():
                 "sweep_ms_per_step": list(ktime["SweepSolver"]),
                 "particles_last": particles[-1] if particles else None,
                 "wall_ms_per_step_device_region": 1e3 * wall_dev / args.steps}
+        if parity is not None:
+            line["parity"] = parity
         if n_gpus == 1 and not args.no_cpu_baseline:
             try:
                 r = run_reference_cpu(args.workload, args.layout, 2, 1, (16, 16, 16))
                 if r:
-                    line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                    line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "command")}
             except Exception as e:  # the baseline is reported, never required
                 line["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(line))

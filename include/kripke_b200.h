@@ -174,6 +174,14 @@ int kb200_sweep(const kb200_sweep_desc *h_descs, int n, kb200_stream_t stream);
  * path did not apply and only the sweep was done: the caller then uses kb200_population. */
 int kb200_sweep_population(const kb200_sweep_desc *h_descs, int n, const double *const *h_w, const double *const *h_volume,
                            double *d_partials, int capacity, int *count, kb200_stream_t stream);
+/* Same again with a hint: h_vol_const[i] > 0 promises that EVERY entry of h_volume[i] equals that value (Kripke's
+ * generator only produces uniform meshes, src/Kripke/Generate/Space.cpp:110-136), so the fused sum needs no volume loads;
+ * h_vol_const[i] == 0 (or h_vol_const == NULL) reads the array. */
+int kb200_sweep_population_uniform(const kb200_sweep_desc *h_descs, int n, const double *const *h_w, const double *const *h_volume,
+                                   const double *h_vol_const, double *d_partials, int capacity, int *count, kb200_stream_t stream);
+/* name of the kernel family that served the most recent sweep call ("irow", "irow+population", "pencil", "pencil+population", "zline", "elem", "tile";
+ * "none" before the first call): the fast paths cover a subset of shapes, and a benchmark line must say which one ran */
+const char *kb200_last_sweep_kernel(void);
 /* *d_result = sum of d_partials[0..n) in index order (fixed-order tree, deterministic) */
 int kb200_population_reduce(const double *d_partials, int n, double *d_result, kb200_stream_t stream);
 

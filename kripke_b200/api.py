@@ -229,6 +229,23 @@ class Problem:
     def field(self, name):
         return np.concatenate([self.chunk(name, c) for c in range(self.num_chunks(name))])
 
+    def norm2(self, name, release=True):
+        """||field||_2 accumulated chunk by chunk (blocked dot products summed with math.fsum), so that multi-GB fields
+        never need more host memory than one chunk; the chunk's host mirror is released after use."""
+        import math
+        parts = []
+        n = 0
+        for c in range(self.num_chunks(name)):
+            v = self.chunk(name, c)
+            n += len(v)
+            for i in range(0, len(v), 1 << 20):
+                b = v[i:i + (1 << 20)]
+                parts.append(float(np.dot(b, b)))
+            del v
+            if release:
+                self.release_host_mirrors(name)
+        return math.sqrt(math.fsum(parts)), n
+
     def device_ptr(self, name, c, will_write=False):
         return host().kripke_b200_field_device_ptr(self.h, name.encode(), c, int(will_write))
 

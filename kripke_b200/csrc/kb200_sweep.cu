@@ -171,11 +171,18 @@ using namespace kb200;
 int kb200_sweep_zline_try(const kb200_sweep_desc *h, int n, const void *d_descs, cudaStream_t st);  // kb200_sweep_zline.cu
 int kb200_sweep_elem_try(const kb200_sweep_desc *h, int n, const void *d_descs, cudaStream_t st);   // kb200_sweep_elem.cu
 int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, const double *const *d_pop_w,
-                         const double *const *d_pop_vol, double *d_pop_partial, int pop_capacity, int *pop_count,
-                         cudaStream_t st);  // kb200_sweep_irow.cu
+                         const double *const *d_pop_vol, const double *h_pop_vol_const, const double *d_pop_vol_const,
+                         double *d_pop_partial, int pop_capacity, int *pop_count, cudaStream_t st);  // kb200_sweep_irow.cu
+int kb200_sweep_pencil_try(const kb200_sweep_desc *h, int n, const void *d_descs, const double *const *d_pop_w,
+                           const double *const *d_pop_vol, const double *d_pop_vol_const, double *d_pop_partial, int pop_capacity,
+                           int *pop_count, cudaStream_t st);  // kb200_sweep_pencil.cu
 
-static int sweep_impl(const kb200_sweep_desc *h, int n, const double *const *h_w, const double *const *h_volume, double *d_partials,
-                      int capacity, int *count, kb200_stream_t stream) {
+// which kernel family handled the most recent kb200_sweep / kb200_sweep_population call of this process
+static const char *g_last_sweep_kernel = "none";
+extern "C" const char *kb200_last_sweep_kernel(void) { return g_last_sweep_kernel; }
+
+static int sweep_impl(const kb200_sweep_desc *h, int n, const double *const *h_w, const double *const *h_volume,
+                      const double *h_vol_const, double *d_partials, int capacity, int *count, kb200_stream_t stream) {
   if (count) *count = 0;
   if (n <= 0) return 0;
   KB_REQUIRE(h, "kb200_sweep: null descriptors");
@@ -194,21 +201,32 @@ static int sweep_impl(const kb200_sweep_desc *h, int n, const double *const *h_w
   const void *d = nullptr;
   int rc = device_descs(h, sizeof(*h) * n, &d, st);
   if (rc) return rc;
-  {  // zone-fastest layouts, ni = 4 * 2^k, default arithmetic; optionally with fused population partials
-    const void *d_w = nullptr, *d_v = nullptr;
+  {  // fast paths, optionally with fused population partials
+    const void *d_w = nullptr, *d_v = nullptr, *d_vc = nullptr;
     if (d_partials && h_w && h_volume && capacity > 0) {
       rc = device_descs(h_w, sizeof(double *) * n, &d_w, st);
       if (rc) return rc;
       rc = device_descs(h_volume, sizeof(double *) * n, &d_v, st);
       if (rc) return rc;
+      if (h_vol_const) {
+        rc = device_descs(h_vol_const, sizeof(double) * n, &d_vc, st);
+        if (rc) return rc;
+      }
     }
-    rc = kb200_sweep_irow_try(h, n, d, (const double *const *)d_w, (const double *const *)d_v, d_w ? d_partials : nullptr, capacity, count, st);
-    if (rc >= 0) return rc;
+    // element-fastest layouts: pencils of zone lines, lanes over elements
+    rc = kb200_sweep_pencil_try(h, n, d, (const double *const *)d_w, (const double *const *)d_v, (const double *)d_vc,
+                                d_w ? d_partials : nullptr, capacity, count, st);
+    if (rc >= 0) { g_last_sweep_kernel = (count && *count > 0) ? "pencil+population" : "pencil"; return rc; }
+    // zone-fastest layouts, ni = 4 * 2^k, default arithmetic
+    rc = kb200_sweep_irow_try(h, n, d, (const double *const *)d_w, (const double *const *)d_v, d_vc ? h_vol_const : nullptr,
+                              (const double *)d_vc, d_w ? d_partials : nullptr, capacity, count, st);
+    if (rc >= 0) { g_last_sweep_kernel = (count && *count > 0) ? "irow+population" : "irow"; return rc; }
   }
   rc = kb200_sweep_zline_try(h, n, d, st);  // zone-fastest layouts with ni % 4 == 0
-  if (rc >= 0) return rc;
+  if (rc >= 0) { g_last_sweep_kernel = "zline"; return rc; }
   rc = kb200_sweep_elem_try(h, n, d, st);  // element-fastest layouts
-  if (rc >= 0) return rc;
+  if (rc >= 0) { g_last_sweep_kernel = "elem"; return rc; }
+  g_last_sweep_kernel = "tile";
   SweepGeom gm;
   gm.layout = h[0].layout; gm.Ds = h[0].Ds; gm.Gs = h[0].Gs; gm.ni = h[0].ni; gm.nj = h[0].nj; gm.nk = h[0].nk;
   gm.ntj = (gm.nj + TJ - 1) / TJ; gm.ntk = (gm.nk + TK - 1) / TK;
@@ -229,11 +247,18 @@ static int sweep_impl(const kb200_sweep_desc *h, int n, const double *const *h_w
 }
 
 extern "C" int kb200_sweep(const kb200_sweep_desc *h, int n, kb200_stream_t stream) {
-  return sweep_impl(h, n, nullptr, nullptr, nullptr, 0, nullptr, stream);
+  return sweep_impl(h, n, nullptr, nullptr, nullptr, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int kb200_sweep_population(const kb200_sweep_desc *h, int n, const double *const *h_w, const double *const *h_volume,
                                       double *d_partials, int capacity, int *count, kb200_stream_t stream) {
   KB_REQUIRE(count, "kb200_sweep_population: null count");
-  return sweep_impl(h, n, h_w, h_volume, d_partials, capacity, count, stream);
+  return sweep_impl(h, n, h_w, h_volume, nullptr, d_partials, capacity, count, stream);
+}
+
+extern "C" int kb200_sweep_population_uniform(const kb200_sweep_desc *h, int n, const double *const *h_w, const double *const *h_volume,
+                                              const double *h_vol_const, double *d_partials, int capacity, int *count,
+                                              kb200_stream_t stream) {
+  KB_REQUIRE(count, "kb200_sweep_population_uniform: null count");
+  return sweep_impl(h, n, h_w, h_volume, h_vol_const, d_partials, capacity, count, stream);
 }

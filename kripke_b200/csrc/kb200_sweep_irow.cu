@@ -147,9 +147,12 @@ __device__ __forceinline__ IItem irow_item(const IGeom &gm, int gi, int t, int w
 
 // PAIR: rows j and j+1 of a k-plane are adjacent in memory, so with an even nj one bulk copy per array brings in
 // TWO rows: half as many copy/mbarrier sequences per zone, two staging slots of a row pair each.
-template <int LR, bool FWD, bool UNI, bool POP, bool PAIR>
+// POPM: 0 = no population sum, 1 = (w*psi)*volume(z) with the zone volumes staged per row, 2 = every zone has the volume
+// `volc` (what Kripke's generator produces): the rows are summed first and scaled by w(d)*volc once per item
+template <int LR, bool FWD, bool UNI, int POPM, bool PAIR>
 __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGeom &gm, const IShared &sh,
-                                           const double *__restrict__ wq, const double *__restrict__ vol) {
+                                           const double *__restrict__ wq, const double *__restrict__ vol, const double volc) {
+  constexpr bool POP = POPM == 1;  // the staged-volume machinery
   constexpr int R = IROW_RING, PD = IROW_PD, NS = PAIR ? 2 : IROW_NS;
   constexpr unsigned RB = PAIR ? 2048u : 1024u;  // bytes of the row block(s) of a warp's ER segments in one slot
   const unsigned SB = gm.sb;
@@ -192,7 +195,10 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
   auto prefetch = [&](const IItem &it, int r, bool ktile0, unsigned qn, unsigned sqn) {
     const bool kload = (w == 0) && !(k_zero && ktile0);
     // rows of a later k tile were written by the tile's predecessor nj row steps earlier
-    if (w == 0 && !ktile0) ir_wait_ge(sh.prod, qn + 1u - (unsigned)nj);
+    if (w == 0 && !ktile0) {
+      ir_wait_ge(sh.prod, qn + 1u - (unsigned)nj);
+      asm volatile("fence.proxy.async.global;" ::: "memory");  // acquired generic-proxy stores -> the bulk copies below
+    }
     const unsigned bar = sbar0 + 8u * sqn;
     if (lane == 0) ir_mb_expect_tx(bar, (kload ? 3u : 2u) * rowb * (unsigned)(32 / LR) + (POP ? rowb : 0u));
     __syncwarp();  // also: every lane is done reading the slot's previous contents
@@ -209,7 +215,10 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
   // PAIR: rows 2*pp and 2*pp+1 (sweep order) of item `it`, whose first step is qn, as one copy per array
   auto prefetch2 = [&](const IItem &it, int pp, bool ktile0, unsigned qn, unsigned sqn) {
     const bool kload = (w == 0) && !(k_zero && ktile0);
-    if (w == 0 && !ktile0) ir_wait_ge(sh.prod, qn + 2u - (unsigned)nj);
+    if (w == 0 && !ktile0) {
+      ir_wait_ge(sh.prod, qn + 2u - (unsigned)nj);
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+    }
     const unsigned bar = sbar0 + 8u * sqn;
     if (lane == 0)
       ir_mb_expect_tx(bar, (kload ? 2u : 1u) * 2u * rowb * (unsigned)(32 / LR) + 2u * rowb * (gm.sig1 ? 1u : (unsigned)(32 / LR)) + (POP ? 2u * rowb : 0u));
@@ -270,7 +279,8 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
     const int kl = t * NW + w;
     const bool k_out_global = (kl == nk - 1) || (w == NW - 1);
     const double cx = sh.cxt[it.d], cz = sh.tzc[it.d] * sh.rdz[it.kz], tyc = sh.tyc[it.d];
-    const double wd = POP ? wq[it.d] : 0.0;  // quadrature weight of this segment's direction
+    const double wd = POPM ? wq[it.d] : 0.0;  // quadrature weight of this segment's direction
+    double psum = 0.0;                        // POPM == 2: sum of this item's psi
     unsigned off = it.off0, ipx = it.ipx0;
     int jz = (jd > 0) ? 0 : nj - 1;
 
@@ -407,6 +417,7 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
 #pragma unroll
           for (int u = 0; u < 4; ++u) pop = fma(wd * p4[u], v4[u], pop);
         }
+        if (POPM == 2) psum += (p4[0] + p4[1]) + (p4[2] + p4[3]);
         if (ls == LR - 1) {
           ds.i_plane[ipx] = fo;
           if (ds.out_plane[0]) ds.out_plane[0][ipx] = fo;
@@ -423,6 +434,8 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
         }
       }
       if (w == NW - 1 && nkt > 1) {  // tile-boundary k faces are in k_plane: tell warp 0
+        // warp 0 fetches them with bulk copies (async proxy): order this lane's generic-proxy stores before them
+        asm volatile("fence.proxy.async.global;" ::: "memory");
         __syncwarp();
         if (lane == 0) ir_st_release(sh.prod, q + 1u);
       }
@@ -447,16 +460,19 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
 #pragma unroll 2  // measured: 1 -> 17.0 ms, 2 -> 16.4 ms, 4 -> 21.8 ms (instruction cache) with the fused population sum
       for (int j = 0; j < nj; ++j) row_step(std::integral_constant<int, -1>{}, j);
     }
+    if (POPM == 2) pop = fma(wd * volc, psum, pop);
     gi = ngi; t = nt;
   }
   return pop;
 }
 
-template <int LR, bool POP, bool PAIR>
+template <int LR, int POPM, bool PAIR>
 __global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sweep_desc *__restrict__ descs, const __grid_constant__ IGeom gm,
                                                              const double *const *__restrict__ pop_w,
                                                              const double *const *__restrict__ pop_vol,
+                                                             const double *__restrict__ pop_vol_const,
                                                              double *__restrict__ pop_partial) {
+  constexpr bool POP = POPM != 0;
   extern __shared__ __align__(16) unsigned char ism[];
   __shared__ kb200_sweep_desc ds;  // the descriptor is read all the time: keep it one LDS away (measured: faster than
   // passing the descriptors by value and reading them through the constant bank)
@@ -499,14 +515,15 @@ __global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sw
   const bool uniform_x = __syncthreads_and(uni) != 0;  // also orders the table writes and the mbarrier inits
 
   const double *wq = POP ? pop_w[blockIdx.y] : nullptr;
-  const double *vol = POP ? pop_vol[blockIdx.y] : nullptr;
+  const double *vol = POPM == 1 ? pop_vol[blockIdx.y] : nullptr;
+  const double volc = POPM == 2 ? pop_vol_const[blockIdx.y] : 0.0;
   double pop;
   if (uniform_x) {
-    if (ds.id > 0) pop = irow_run<LR, true, true, POP, PAIR>(ds, gm, sh, wq, vol);
-    else pop = irow_run<LR, false, true, POP, PAIR>(ds, gm, sh, wq, vol);
+    if (ds.id > 0) pop = irow_run<LR, true, true, POPM, PAIR>(ds, gm, sh, wq, vol, volc);
+    else pop = irow_run<LR, false, true, POPM, PAIR>(ds, gm, sh, wq, vol, volc);
   } else {
-    if (ds.id > 0) pop = irow_run<LR, true, false, POP, PAIR>(ds, gm, sh, wq, vol);
-    else pop = irow_run<LR, false, false, POP, PAIR>(ds, gm, sh, wq, vol);
+    if (ds.id > 0) pop = irow_run<LR, true, false, POPM, PAIR>(ds, gm, sh, wq, vol, volc);
+    else pop = irow_run<LR, false, false, POPM, PAIR>(ds, gm, sh, wq, vol, volc);
   }
 
   if (POP) {  // fixed-order block reduction: lanes, then warps
@@ -527,25 +544,31 @@ using namespace kb200;
 
 template <int LR, bool PAIR>
 static int launch_irow(const kb200_sweep_desc *d_descs, int n, const IGeom &gm, int cps, size_t smem, const double *const *pw,
-                       const double *const *pv, double *pp, cudaStream_t st) {
+                       const double *const *pv, const double *pvc, double *pp, cudaStream_t st) {
   dim3 grid(cps, n, 1);
-  if (pp) {
-    auto k = sweep_irow_kernel<LR, true, PAIR>;
+  if (pp && pvc) {
+    auto k = sweep_irow_kernel<LR, 2, PAIR>;
     KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, pw, pv, pp);
+    k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, pw, pv, pvc, pp);
+  } else if (pp) {
+    auto k = sweep_irow_kernel<LR, 1, PAIR>;
+    KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, pw, pv, nullptr, pp);
   } else {
-    auto k = sweep_irow_kernel<LR, false, PAIR>;
+    auto k = sweep_irow_kernel<LR, 0, PAIR>;
     KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, nullptr, nullptr, nullptr);
+    k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, nullptr, nullptr, nullptr, nullptr);
   }
   return post_launch("sweep_irow");
 }
 
 // Returns 0 if the batch was handled, -1 if this path does not apply (caller falls back), >0 on error.
 // pop_* (optional, device pointer tables of n entries + a scratch of pop_capacity doubles): fused population partials.
+// h_pop_vol_const / d_pop_vol_const (optional, host and device copies of n doubles): > 0 = every zone of that subdomain has
+// this volume; the uniform path is taken when that holds for all n subdomains.
 int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, const double *const *d_pop_w,
-                         const double *const *d_pop_vol, double *d_pop_partial, int pop_capacity, int *pop_count,
-                         cudaStream_t st) {
+                         const double *const *d_pop_vol, const double *h_pop_vol_const, const double *d_pop_vol_const,
+                         double *d_pop_partial, int pop_capacity, int *pop_count, cudaStream_t st) {
   const int layout = h[0].layout;
   if (pop_count) *pop_count = 0;
   if (layout != 0 && layout != 2) return -1;
@@ -585,11 +608,13 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
   const unsigned rowb = 8u * (unsigned)ni;
   const char *pe = getenv("KB200_IROW_PAIR");
   bool pair = (nj % 2 == 0) && nj >= 4 && !(pe && pe[0] == '0');
+  bool volu = d_pop_partial && h_pop_vol_const && d_pop_vol_const;
+  for (int i = 0; volu && i < n; ++i) volu = h_pop_vol_const[i] > 0.0;
   size_t smem = 0;
   for (;;) {
     const unsigned rb = pair ? 2048u : 1024u;
     gm.vol_off = rb + ((pair && gm.sig1) ? 2u * rowb : rb);  // a shared sigt row pair takes 2*rowb instead of a full block
-    gm.sb = gm.vol_off + (d_pop_partial ? (pair ? 2u : 1u) * rowb : 0u);
+    gm.sb = gm.vol_off + ((d_pop_partial && !volu) ? (pair ? 2u : 1u) * rowb : 0u);
     smem = (size_t)IROW_RING * (gm.NW + 1) * rb + (size_t)4 * 1024 + (size_t)gm.NW * (pair ? 2 : IROW_NS) * gm.sb +
            ((size_t)4 * gm.Ds + nj + nk + 32 + 2 * (gm.NW + 1) * IROW_RING + gm.NW * IROW_NS + 2) * sizeof(double);
     if (smem <= 226 * 1024 || !pair) break;
@@ -609,8 +634,9 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
   if (pp && (long long)cps * n > pop_capacity) pp = nullptr;
   if (pop_count) *pop_count = pp ? cps * n : 0;
   const kb200_sweep_desc *dd = (const kb200_sweep_desc *)d_descs;
-#define IROW_LAUNCH(LR_) return pair ? launch_irow<LR_, true>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st) \
-                                    : launch_irow<LR_, false>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pp, st)
+  const double *pvc = (pp && volu) ? d_pop_vol_const : nullptr;
+#define IROW_LAUNCH(LR_) return pair ? launch_irow<LR_, true>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pvc, pp, st) \
+                                    : launch_irow<LR_, false>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pvc, pp, st)
   switch (LR) {
     case 1: IROW_LAUNCH(1);
     case 2: IROW_LAUNCH(2);

@@ -341,12 +341,17 @@ class FieldStorageBase : public DomainVar {
   // device pointer for a kernel that defines the whole chunk (no upload, no memset)
   void *devPtrOverwrite(SdomId sdom_id);
   void releaseHostMirrors();
+  // fields of doubles: the value if every element of the chunk is the same positive number, else 0; looked at on the
+  // host once per content (write epoch) of the chunk
+  double uniformPositiveValue(SdomId sdom_id);
  protected:
   struct Chunk {
     void *dev = nullptr;
     void *host = nullptr;
     bool host_valid = false, dev_valid = false, zero_pending = false;
     unsigned long write_epoch = 0;
+    unsigned long uniform_epoch = ~0ul;  // write epoch uniform_value was computed for
+    double uniform_value = 0.0;
   };
   void materializeZero(Chunk &c, size_t bytes);
   Set const *m_set;

@@ -413,6 +413,21 @@ void FieldStorageBase::releaseHostMirrors() {
     if (c.host && c.dev_valid) { free(c.host); c.host = nullptr; c.host_valid = false; }
   }
 }
+double FieldStorageBase::uniformPositiveValue(SdomId sdom_id) {
+  size_t ci = m_subdomain_to_chunk[*sdom_id];
+  if (m_elem_size != sizeof(double)) return 0.0;
+  if (m_chunks[ci].uniform_epoch != m_chunks[ci].write_epoch) {
+    const double *v = (const double *)hostPtr(sdom_id, false);
+    Chunk &c = m_chunks[ci];
+    const size_t n = m_chunk_to_size[ci];
+    double u = n ? v[0] : 0.0;
+    for (size_t i = 1; i < n && u > 0.0; ++i)
+      if (v[i] != u) u = 0.0;
+    c.uniform_value = (u > 0.0) ? u : 0.0;
+    c.uniform_epoch = c.write_epoch;
+  }
+  return m_chunks[ci].uniform_value;
+}
 void FieldStorageBase::materializeZero(Chunk &c, size_t bytes) {
   // the pending zero-fill becomes real, on whichever side is being touched
   if (c.host) { memset(c.host, 0, bytes); c.host_valid = true; }

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
 
 using namespace Kripke;
 using namespace Kripke::Core;
@@ -354,10 +355,16 @@ void Kripke::Kernel::sweepSubdomains(DataStore &data_store, std::vector<SdomId> 
     auto &f_w = data_store.getVariable<Field_Direction2Double>("quadrature/w");
     auto &f_vol = data_store.getVariable<Field_Zone2Double>("volume");
     std::vector<const double *> pw, pv;
-    for (SdomId s : sdom_ids) { pw.push_back(f_w.devicePtrConst(s)); pv.push_back(f_vol.devicePtrConst(s)); }
+    std::vector<double> vc;
+    for (SdomId s : sdom_ids) {
+      pw.push_back(f_w.devicePtrConst(s));
+      // > 0: every zone of the chunk has this volume (all the generator produces, Generate/Space.cpp:110-136)
+      vc.push_back(f_vol.uniformPositiveValue(s));
+      pv.push_back(f_vol.devicePtrConst(s));
+    }
     int count = 0;
-    KB200_CALL(kb200_sweep_population(descs.data(), (int)descs.size(), pw.data(), pv.data(), g_pop.d_partials + g_pop.used,
-                                      g_pop.capacity - g_pop.used, &count, nullptr));
+    KB200_CALL(kb200_sweep_population_uniform(descs.data(), (int)descs.size(), pw.data(), pv.data(), vc.data(),
+                                              g_pop.d_partials + g_pop.used, g_pop.capacity - g_pop.used, &count, nullptr));
     if (count > 0) {
       g_pop.used += count;
       for (SdomId s : sdom_ids) {

@@ -28,6 +28,20 @@ def test_reference_arm_prints_one_contract_line(native_built):
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
+    # honesty: the line says which command line the reference really ran and that it was a sample, not the named block
+    assert "--zones 4,4,4" in d["command"] and d["sample_zones"] == [4, 4, 4] and d["sample_is_full_workload"] is False
+    assert "--zones" not in d["config"]["workload"]
+
+
+def test_reference_sample_is_sized_by_host_memory_and_time():
+    sys.path.insert(0, ROOT)
+    import bench
+    z = bench.reference_sample_zones("config2", 20, 5)
+    zones, groups, dirs = bench.WORKLOADS["config2"][:3]
+    assert all(a <= b for a, b in zip(z, zones)) and z[0] * z[1] * z[2] >= 16 ** 3
+    unknowns = z[0] * z[1] * z[2] * groups * dirs
+    assert unknowns * 18.5 <= 0.9 * bench.host_mem_available_gb() * 1e9 or z == (16, 16, 16)
+    assert bench.reference_sample_zones("config1", 2, 1) == (16, 16, 16)
 
 
 def test_reference_arm_other_ranks_exit_quietly(native_built):

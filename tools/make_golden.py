@@ -34,6 +34,12 @@ CASES = {
     "R2_legendre0": "--zones 6,6,6 --groups 2 --quad 8 --legendre 0 --gset 1 --niter 2",
     "R3_custom_xs": "--zones 8,8,8 --groups 4 --quad 16 --legendre 2 --sigt 0.2,0.001,0.3 --sigs 0.1,0.0005,0.02 --niter 4",
 }
+# BASELINE config 3 at full size (15 GB of fields, minutes on the host) and the largest slab of BASELINE config 2
+# this container's 62 GB host can hold (config 2's groups, directions and 64 x 64 zone cross-section, half its k extent)
+BIG_CASES = {
+    "G7_config3_full": "--zones 32,32,32 --groups 128 --quad 128 --legendre 9 --niter 2",
+    "G8_config2_half_slab": "--zones 64,64,32 --groups 64 --quad 192 --legendre 4 --niter 2",
+}
 # every storage order on one decomposed problem
 for lay in ["DGZ", "DZG", "GDZ", "GZD", "ZDG", "ZGD"]:
     CASES[f"L_{lay}"] = f"--zones 12,8,8 --groups 8 --quad 32 --legendre 3 --gset 2 --dset 8 --zset 2,1,2 --layout {lay} --niter 3"
@@ -54,12 +60,25 @@ def run_case(args):
 
 
 def main():
+    """no arguments: regenerate the small cases; `make_golden.py NAME...`: (re)generate only the named cases (the big ones
+    are only run by name) and merge them into the existing file."""
     if not os.path.exists(REF):
         sys.exit("build the reference first: make -C oracle ref")
-    out = {name: run_case(args) for name, args in CASES.items()}
+    path = os.path.join(ROOT, "tests", "golden", "reference_goldens.json")
+    allc = dict(CASES, **BIG_CASES)
+    if len(sys.argv) > 1:
+        with open(path) as f:
+            out = json.load(f)
+        for name in sys.argv[1:]:
+            out[name] = run_case(allc[name])
+    else:
+        out = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                out = {k: v for k, v in json.load(f).items() if k in BIG_CASES}
+        out.update({name: run_case(args) for name, args in CASES.items()})
     for name, r in out.items():
         print(name, "%.17g" % r["particles"][-1])
-    path = os.path.join(ROOT, "tests", "golden", "reference_goldens.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     print("wrote", path)
