@@ -15,7 +15,9 @@
  *    a few private scratch buffers that live until kb200_finalize: the device copies of the
  *    descriptors, the per-zone material fractions of kb200_scattering, and -- only for the
  *    nestings whose moments are not zone-fastest -- two transposed copies of a moments chunk.
- *    kb200_free keeps blocks up to 64 MB in a pool for the next kb200_alloc of the same size.
+ *    kb200_free keeps blocks up to 64 MB in a pool for the next kb200_alloc of the same size; while streams created
+ *    with kb200_stream_create exist it synchronises the device first (like cudaFree), otherwise the library stream orders
+ *    the old and the new owner.
  *  - `layout` is the reference's LayoutV value: 0=DGZ 1=DZG 2=GDZ 3=GZD 4=ZDG 5=ZGD
  *    (src/Kripke/ArchLayout.h:92-101); storage orders follow src/Kripke/VarTypes.h:73-101.
  *  - `stream` is a cudaStream_t passed as void* (NULL = the library's default stream).
@@ -54,6 +56,7 @@ int kb200_upload(void *d_dst, const void *h_src, size_t bytes, kb200_stream_t st
 int kb200_download(void *h_dst, const void *d_src, size_t bytes, kb200_stream_t stream);
 int kb200_copy(void *d_dst, const void *d_src, size_t bytes, kb200_stream_t stream); /* Kernel::kCopy, Kernel.h:60-81; ParallelComm.cpp:149-161 */
 int kb200_fill_f64(double *d_ptr, double value, size_t n, kb200_stream_t stream);    /* Kernel::kConst, Kernel.h:37-55 */
+int kb200_memset(void *d_ptr, int byte_value, size_t bytes, kb200_stream_t stream);  /* kConst on fields of any element size */
 int kb200_stream_create(kb200_stream_t *stream);
 int kb200_stream_destroy(kb200_stream_t stream);
 int kb200_stream_sync(kb200_stream_t stream);
@@ -205,6 +208,21 @@ int kb200_comm_send(const double *d_buf, size_t count, int peer, kb200_stream_t 
 int kb200_comm_recv(double *d_buf, size_t count, int peer, kb200_stream_t stream);       /* MPI_Irecv, ParallelComm.cpp:106 */
 int kb200_comm_allreduce_sum_f64(double *d_buf, size_t count, kb200_stream_t stream);    /* Comm.h:161-166 */
 int kb200_comm_allreduce_sum_i64(long long *d_buf, size_t count, kb200_stream_t stream); /* Comm.h:121-130 */
+
+int kb200_comm_allgather(const void *h_send, size_t bytes_per_rank, void *h_recv);       /* setup: Comm.h / Set.cpp all-gathers */
+int kb200_comm_barrier(kb200_stream_t stream);                                           /* stream-ordered, no host sync */
+
+/* ---- exchange over NVLink peer memory (CUDA IPC), the path SweepSolver uses between GPUs of one node -------------
+ * The receiver exports its plane chunks (and one array of flags) once; the sender maps them and passes the mapped
+ * pointer as kb200_sweep_desc.out_plane, so the sweep kernel itself stores the outgoing faces into the downwind
+ * subdomain's plane chunk on the other GPU (ParallelComm.cpp:99-107 "receive straight into the plane chunk", :170-178).
+ * kb200_p2p_signal raises flags in peer memory after all earlier work of the stream, kb200_p2p_wait holds later work of
+ * the stream until local flags have reached a value (MPI_Testany, :222-230) -- device side, no host synchronisation. */
+int kb200_ipc_export(const void *d_ptr, void *handle64);        /* d_ptr: base of a kb200_alloc block */
+int kb200_ipc_open(const void *handle64, void **d_peer_ptr);
+int kb200_ipc_close(void *d_peer_ptr);
+int kb200_p2p_signal(unsigned *const *h_flags, int n, unsigned value, kb200_stream_t stream);
+int kb200_p2p_wait(const unsigned *const *h_flags, int n, unsigned value, kb200_stream_t stream);
 
 /* ---- micro-benchmarks used for the roofline denominators (bench.py / tools) ------------------ */
 int kb200_peak_fp64_gflops(int use_dmma, int iters, double *gflops); /* DFMA / DMMA issue peak */

@@ -164,6 +164,7 @@ struct Nccl {
   int (*Send)(const void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, nccl_comm, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
@@ -191,6 +192,7 @@ static int nccl_load() {
   SYM(Send, "ncclSend");
   SYM(Recv, "ncclRecv");
   SYM(AllReduce, "ncclAllReduce");
+  SYM(AllGather, "ncclAllGather");
   SYM(GroupStart, "ncclGroupStart");
   SYM(GroupEnd, "ncclGroupEnd");
   SYM(GetErrorString, "ncclGetErrorString");
@@ -291,6 +293,7 @@ int kb200_device_info(char *name, size_t name_len, int *sms, int *maj, int *min,
 // and handed out again; all work runs on the library's stream, so reuse is stream-ordered.
 namespace {
 constexpr size_t kPoolMaxBlock = 64u << 20, kPoolMaxTotal = 4ull << 30;
+std::atomic<int> g_user_streams{0};  // streams handed out by kb200_stream_create and not yet destroyed
 std::mutex g_pool_mutex;
 std::unordered_map<void *, size_t> g_pool_sizes;            // live blocks that may be pooled when freed
 std::unordered_map<size_t, std::vector<void *>> g_pool_free;
@@ -337,6 +340,11 @@ int kb200_alloc(size_t bytes, void **p) {
 }
 int kb200_free(void *p) {
   if (!p) return 0;
+  // A pooled block can be handed to its next owner at once.  That is only safe if no work that still uses it is
+  // outstanding: work on the library stream is ordered with the next owner's work on the same stream, but as soon as the
+  // caller has created streams of its own (kb200_stream_create) a kernel on one of them may still be running -- then
+  // behave like cudaFree and wait for the device first.
+  if (g_user_streams.load() > 0) KB_CUDA(cudaDeviceSynchronize());
   {
     std::lock_guard<std::mutex> lock(g_pool_mutex);
     auto it = g_pool_sizes.find(p);
@@ -392,10 +400,19 @@ int kb200_stream_create(kb200_stream_t *s) {
   cudaStream_t st;
   KB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   *s = (kb200_stream_t)st;
+  ++g_user_streams;
   return 0;
 }
 int kb200_stream_destroy(kb200_stream_t s) {
-  if (s) KB_CUDA(cudaStreamDestroy((cudaStream_t)s));
+  if (s) {
+    KB_CUDA(cudaStreamDestroy((cudaStream_t)s));
+    --g_user_streams;
+  }
+  return 0;
+}
+int kb200_memset(void *p, int byte_value, size_t bytes, kb200_stream_t s) {
+  if (!bytes) return 0;
+  KB_CUDA(cudaMemsetAsync(p, byte_value, bytes, resolve_stream(s)));
   return 0;
 }
 int kb200_stream_sync(kb200_stream_t s) {
@@ -500,6 +517,35 @@ int kb200_comm_allreduce_sum_f64(double *buf, size_t count, kb200_stream_t s) {
 int kb200_comm_allreduce_sum_i64(long long *buf, size_t count, kb200_stream_t s) {
   if (!g_nccl.comm || g_nccl.nranks == 1) return 0;
   KB_NCCL(g_nccl.AllReduce(buf, buf, count, NCCL_INT64, NCCL_SUM, g_nccl.comm, resolve_stream(s)));
+  return 0;
+}
+
+// host buffers: h_recv[r * bytes .. (r+1) * bytes) = rank r's h_send (setup-time exchange of IPC handles, MPI_Allgather's role)
+int kb200_comm_allgather(const void *h_send, size_t bytes, void *h_recv) {
+  if (!g_nccl.comm || g_nccl.nranks == 1) {
+    memcpy(h_recv, h_send, bytes);
+    return 0;
+  }
+  if (!bytes) return 0;
+  cudaStream_t st = resolve_stream(nullptr);
+  unsigned char *d = nullptr;
+  KB_CUDA(cudaMalloc(&d, bytes * (size_t)(g_nccl.nranks + 1)));
+  KB_CUDA(cudaMemcpyAsync(d, h_send, bytes, cudaMemcpyHostToDevice, st));
+  KB_NCCL(g_nccl.AllGather(d, d + bytes, bytes, 0 /* ncclInt8 */, g_nccl.comm, st));
+  KB_CUDA(cudaMemcpyAsync(h_recv, d + bytes, bytes * (size_t)g_nccl.nranks, cudaMemcpyDeviceToHost, st));
+  KB_CUDA(cudaStreamSynchronize(st));
+  KB_CUDA(cudaFree(d));
+  return 0;
+}
+// stream-ordered barrier over all ranks (a one-element all-reduce)
+int kb200_comm_barrier(kb200_stream_t s) {
+  if (!g_nccl.comm || g_nccl.nranks == 1) return 0;
+  static long long *d_one = nullptr;
+  if (!d_one) {
+    KB_CUDA(cudaMalloc(&d_one, sizeof(long long)));
+    KB_CUDA(cudaMemset(d_one, 0, sizeof(long long)));
+  }
+  KB_NCCL(g_nccl.AllReduce(d_one, d_one, 1, NCCL_INT64, NCCL_SUM, g_nccl.comm, resolve_stream(s)));
   return 0;
 }
 

@@ -5,7 +5,11 @@
 
 #include <algorithm>
 #include <cstring>
+#include <ctype.h>
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
 
 using namespace Kripke;
 using namespace Kripke::Core;
@@ -120,27 +124,42 @@ void Comm::init(int *, char ***) {
   int cr = 0, cn = 1;
   kb200_comm_rank(&cr, &cn);
   if (g_world_size > 1 && cn != g_world_size) {
-    const char *port = getenv("MASTER_PORT");
-    std::string path = std::string("/tmp/kripke_b200_ncclid_") + (port ? port : "0");
+    // The file lives in a directory only this user can enter and is named after this launch (the launcher's run id and
+    // pid: every rank of one torchrun has the same parent), so a leftover of a crashed run is never read; it is created
+    // exclusively (no symlink following) under a temporary name and renamed when complete.
+    const char *port = getenv("MASTER_PORT"), *run = getenv("TORCHELASTIC_RUN_ID");
+    char nonce[96];
+    snprintf(nonce, sizeof(nonce), "%s_%ld", (run && *run) ? run : "none", (long)getppid());
+    for (char *c = nonce; *c; ++c)
+      if (!isalnum((unsigned char)*c) && *c != '_' && *c != '-') *c = '_';
+    std::string dir = std::string("/tmp/kripke_b200_") + std::to_string((long)getuid());
+    mkdir(dir.c_str(), 0700);
+    struct stat sb;
+    KRIPKE_ASSERT(lstat(dir.c_str(), &sb) == 0 && S_ISDIR(sb.st_mode) && sb.st_uid == getuid() && (sb.st_mode & 077) == 0,
+                  "%s is not a private directory of this user\n", dir.c_str());
+    std::string path = dir + "/ncclid_" + (port ? port : "0") + "_" + nonce;
     unsigned char id[128];
     if (g_world_rank == 0) {
       KB200_CALL(kb200_comm_unique_id(id));
       std::string tmp = path + ".tmp";
-      FILE *f = fopen(tmp.c_str(), "wb");
-      KRIPKE_ASSERT(f != nullptr, "cannot write %s\n", tmp.c_str());
-      fwrite(id, 1, sizeof(id), f);
-      fclose(f);
+      unlink(tmp.c_str());
+      unlink(path.c_str());
+      int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+      KRIPKE_ASSERT(fd >= 0, "cannot create %s\n", tmp.c_str());
+      ssize_t w = write(fd, id, sizeof(id));
+      close(fd);
+      KRIPKE_ASSERT(w == (ssize_t)sizeof(id), "short write of %s\n", tmp.c_str());
       rename(tmp.c_str(), path.c_str());
     } else {
-      FILE *f = nullptr;
-      for (int tries = 0; tries < 6000 && !f; ++tries) {
-        f = fopen(path.c_str(), "rb");
-        if (!f) { struct timespec ts = {0, 10000000}; nanosleep(&ts, nullptr); }
+      int fd = -1;
+      for (int tries = 0; tries < 6000 && fd < 0; ++tries) {
+        fd = open(path.c_str(), O_RDONLY | O_NOFOLLOW);
+        if (fd < 0) { struct timespec ts = {0, 10000000}; nanosleep(&ts, nullptr); }
       }
-      KRIPKE_ASSERT(f != nullptr, "timed out waiting for %s\n", path.c_str());
-      size_t got = fread(id, 1, sizeof(id), f);
-      fclose(f);
-      KRIPKE_ASSERT(got == sizeof(id), "short read of %s\n", path.c_str());
+      KRIPKE_ASSERT(fd >= 0, "timed out waiting for %s\n", path.c_str());
+      ssize_t got = read(fd, id, sizeof(id));
+      close(fd);
+      KRIPKE_ASSERT(got == (ssize_t)sizeof(id), "short read of %s\n", path.c_str());
     }
     KB200_CALL(kb200_comm_init(g_world_rank, g_world_size, id));
     if (g_world_rank == 0) {  // everyone has joined once init returns
@@ -431,7 +450,7 @@ double FieldStorageBase::uniformPositiveValue(SdomId sdom_id) {
 void FieldStorageBase::materializeZero(Chunk &c, size_t bytes) {
   // the pending zero-fill becomes real, on whichever side is being touched
   if (c.host) { memset(c.host, 0, bytes); c.host_valid = true; }
-  if (c.dev) { KB200_CALL(kb200_fill_f64((double *)c.dev, 0.0, (bytes + 7) / 8, nullptr)); c.dev_valid = true; }
+  if (c.dev) { KB200_CALL(kb200_memset(c.dev, 0, bytes, nullptr)); c.dev_valid = true; }
   if (!c.host && !c.dev) { c.host_valid = c.dev_valid = false; }
   c.zero_pending = false;
 }
@@ -469,7 +488,7 @@ void *FieldStorageBase::devPtr(SdomId sdom_id, bool will_write) {
     c.dev_valid = false;
   }
   if (c.zero_pending) {
-    KB200_CALL(kb200_fill_f64((double *)c.dev, 0.0, (bytes + 7) / 8, nullptr));
+    KB200_CALL(kb200_memset(c.dev, 0, bytes, nullptr));  // exact byte count: 4-byte fields may have an odd length
     c.dev_valid = true;
     c.host_valid = false;
     c.zero_pending = false;
