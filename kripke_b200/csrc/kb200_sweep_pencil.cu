@@ -327,6 +327,9 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
       int d;
       if (more) slice_elem(nit - npr * gm.nslices, eo, so, ipo, njp, nkp, d);
       nb = eo + izn * fz; nsb = so + izn * sz;
+      // the operand requests below are unconditional (a predicated load would have to merge with the old register value,
+      // which costs a copy that waits for the load): with nothing to fetch they re-read the current zone column
+      if (!more) { nb = b; nsb = sb; }
     }
     const unsigned wb = mb - 8u * lane;  // this warp's block
     if (fl & (F_JB | F_KB)) { p_cp_async_wait(); __syncwarp(); }
@@ -374,10 +377,8 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
           if (!FULL && !(lmask >> l & 1u)) continue;
           const double cyj = p_lds(mb + OC + (2 + jl) * 256);
           const double r = R[l], st = S[l], fi = FI[l], fk = fko[jl];
-          if (more) {  // operands of the next step of this line
-            R[l] = p_ldg(rhs_b + (zrow[l] * fz + nb));
-            S[l] = __ldg(sigt_b + (zrow[l] * sz + nsb));
-          }
+          R[l] = p_ldg(rhs_b + (zrow[l] * fz + nb));  // operands of the next step of this line
+          S[l] = __ldg(sigt_b + (zrow[l] * sz + nsb));
           const double den = __dadd_rn(__dadd_rn(__dadd_rn(cxu, cyj), czk), st);
           double num = __dadd_rn(r, __dmul_rn(fi, cxu));
           num = __dadd_rn(num, __dmul_rn(fj, cyj));
@@ -408,10 +409,8 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
           const double e2 = fma(e1, e1, e1);
           const double rc = fma(y, e2, y);
           const double a = fma(FI[l], cxu, R[l]) * rc;
-          if (more) {  // operands of the next step of this line
-            R[l] = p_ldg(rhs_b + (zrow[l] * fz + nb));
-            S[l] = __ldg(sigt_b + (zrow[l] * sz + nsb));
-          }
+          R[l] = p_ldg(rhs_b + (zrow[l] * fz + nb));  // operands of the next step of this line
+          S[l] = __ldg(sigt_b + (zrow[l] * sz + nsb));
           q[jl] = fma(fko[jl], czk * rc, a);
           cyr[jl] = cyj * rc;
         }

@@ -588,6 +588,36 @@ void kCopy(FieldType &field_dst, FieldType &field_src) {
 }
 }  // namespace Kernel
 
+// ---- exchange over NVLink peer memory (one process per GPU, same node) -------------------------------------------
+// Owned by the DataStore ("kb200/p2p"): the plane chunks of this rank that an off-rank upwind subdomain writes are
+// exported once (CUDA IPC), the peers' chunks this rank writes are mapped, and every (subdomain, dimension) face has a
+// flag in the receiver's memory.  The sweep kernel stores outgoing faces straight into the mapped chunk
+// (kb200_sweep_desc.out_plane); PeerExchange::signal / wait order the two GPUs' streams.  Replaces the MPI_Irecv /
+// MPI_Isend / MPI_Testany triple of src/Kripke/ParallelComm.cpp:61-251.
+class PeerExchange : public Core::BaseVar {
+ public:
+  // collective over all ranks; returns nullptr when peer mapping is unavailable (then NCCL send/recv is used)
+  static PeerExchange *get(Core::DataStore &data_store);
+  ~PeerExchange() override;
+  bool usable() const { return m_usable; }
+  // mapped pointer of the downwind subdomain's plane chunk on its GPU (nullptr: on-rank or no neighbour)
+  double *outPlane(SdomId sdom_id, int dim) const { return m_out_ptr[3 * (size_t)*sdom_id + dim]; }
+  void beginSweep() { ++m_epoch; }
+  // raise the flags of the faces the given subdomains have just produced / hold the stream until the faces the given
+  // subdomains need have arrived
+  void signal(std::vector<SdomId> const &produced);
+  void wait(std::vector<SdomId> const &needed);
+ private:
+  PeerExchange() = default;
+  bool m_usable = false;
+  unsigned m_epoch = 0;
+  unsigned *m_flags = nullptr;              // [3 * local subdomains] on this GPU
+  std::vector<double *> m_out_ptr;          // [3 * local subdomains] mapped downwind chunk
+  std::vector<unsigned *> m_out_flag;       // [3 * local subdomains] mapped flag of that face
+  std::vector<char> m_in_offrank;           // [3 * local subdomains] the upwind face comes from another rank
+  std::vector<void *> m_opened;             // mapped bases to close
+};
+
 // ---- exchange: src/Kripke/ParallelComm.h ------------------------------------------------------------------------
 class ParallelComm {
  public:

@@ -315,6 +315,8 @@ void Kripke::Kernel::sweepSubdomains(DataStore &data_store, std::vector<SdomId> 
                                      &data_store.getVariable<Field_KPlane>("k_plane")};
   auto &f_down = data_store.getVariable<Field_Adjacency>("downwind");
 
+  PeerExchange *px = (deliver_downwind && comm.size() > 1) ? PeerExchange::get(data_store) : nullptr;
+  if (px && !px->usable()) px = nullptr;
   std::vector<kb200_sweep_desc> descs;
   for (SdomId s : sdom_ids) {
     kb200_sweep_desc d;
@@ -347,6 +349,8 @@ void Kripke::Kernel::sweepSubdomains(DataStore &data_store, std::vector<SdomId> 
       if (deliver_downwind && down[dim] >= 0 && pspace.globalSdomIdToRank(GlobalSdomId(down[dim])) == (int)comm.rank()) {
         SdomId sd = pspace.globalSdomIdToSdomId(GlobalSdomId(down[dim]));
         d.out_plane[dim] = planes[dim]->devicePtrOverwrite(sd);  // folds ParallelComm::postSends' on-rank copy
+      } else if (px && down[dim] >= 0) {
+        d.out_plane[dim] = px->outPlane(s, dim);  // the downwind chunk on another GPU, mapped over NVLink
       }
     }
     descs.push_back(d);

@@ -74,6 +74,136 @@ void runExchange(std::vector<Message> &msgs) {
 
 }  // namespace
 
+// ---- PeerExchange ------------------------------------------------------------------------------------------------------
+namespace {
+struct ExportEntry {  // one plane chunk this rank lets a peer write
+  long gid;           // global id of the receiving subdomain
+  int dim, pad;
+  unsigned char handle[64];
+};
+bool peerExchangeWanted() {
+  const char *e = getenv("KB200_P2P");
+  return !(e && e[0] == '0');
+}
+}  // namespace
+
+PeerExchange *PeerExchange::get(DataStore &ds) {
+  if (ds.isVariableType<PeerExchange>("kb200/p2p")) return &ds.getVariable<PeerExchange>("kb200/p2p");
+  PeerExchange *px = new PeerExchange();
+  ds.addVariable("kb200/p2p", px);
+  Comm comm;
+  if (comm.size() <= 1 || !peerExchangeWanted()) return px;
+  auto &pspace = ds.getVariable<PartitionSpace>("pspace");
+  FieldStorage<double> *planes[3] = {&ds.getVariable<Field_IPlane>("i_plane"), &ds.getVariable<Field_JPlane>("j_plane"),
+                                     &ds.getVariable<Field_KPlane>("k_plane")};
+  auto &f_up = ds.getVariable<Field_Adjacency>("upwind");
+  auto &f_down = ds.getVariable<Field_Adjacency>("downwind");
+  const long *l2g = ds.getVariable<Field_SdomId2GlobalSdomId>("SdomId2GlobalSdomId").getDataConst(SdomId(0));
+  const size_t nlocal = pspace.getNumSubdomains(SPACE_PQR);
+  const int me = (int)comm.rank(), nranks = (int)comm.size();
+  px->m_out_ptr.assign(3 * nlocal, nullptr);
+  px->m_out_flag.assign(3 * nlocal, nullptr);
+  px->m_in_offrank.assign(3 * nlocal, 0);
+
+  // what this rank exports: its flags, and every plane chunk with an off-rank upwind neighbour
+  KB200_CALL(kb200_alloc(3 * nlocal * sizeof(unsigned), (void **)&px->m_flags));
+  KB200_CALL(kb200_memset(px->m_flags, 0, 3 * nlocal * sizeof(unsigned), nullptr));
+  std::vector<ExportEntry> mine;
+  int ok = 1;
+  for (size_t s = 0; s < nlocal; ++s) {
+    const long *up = f_up.getDataConst(SdomId((long)s));
+    for (int dim = 0; dim < 3; ++dim) {
+      if (up[dim] < 0 || pspace.globalSdomIdToRank(GlobalSdomId(up[dim])) == me) continue;
+      px->m_in_offrank[3 * s + dim] = 1;
+      ExportEntry e;
+      memset(&e, 0, sizeof(e));
+      e.gid = l2g[s];
+      e.dim = dim;
+      if (kb200_ipc_export(planes[dim]->devicePtr(SdomId((long)s)), e.handle) != 0) ok = 0;
+      mine.push_back(e);
+    }
+  }
+  unsigned char flag_handle[64];
+  memset(flag_handle, 0, sizeof(flag_handle));
+  if (kb200_ipc_export(px->m_flags, flag_handle) != 0) ok = 0;
+  KB200_CALL(kb200_stream_sync(nullptr));
+
+  // gather: [ok, count] of every rank, then the flag handles, then the (padded) tables
+  std::vector<int> head(2 * (size_t)nranks);
+  const int myhead[2] = {ok, (int)mine.size()};
+  KB200_CALL(kb200_comm_allgather(myhead, sizeof(myhead), head.data()));
+  int maxn = 0;
+  bool all_ok = true;
+  for (int r = 0; r < nranks; ++r) { all_ok = all_ok && head[2 * r] != 0; maxn = std::max(maxn, head[2 * r + 1]); }
+  std::vector<unsigned char> flag_handles(64 * (size_t)nranks);
+  KB200_CALL(kb200_comm_allgather(flag_handle, 64, flag_handles.data()));
+  mine.resize((size_t)std::max(maxn, 1));
+  std::vector<ExportEntry> all((size_t)std::max(maxn, 1) * nranks);
+  KB200_CALL(kb200_comm_allgather(mine.data(), mine.size() * sizeof(ExportEntry), all.data()));
+
+  // map what this rank writes: the downwind chunk and its flag, for every off-rank downwind face
+  std::vector<unsigned *> peer_flags((size_t)nranks, nullptr);
+  int mapped = all_ok ? 1 : 0;
+  for (size_t s = 0; s < nlocal && mapped; ++s) {
+    const long *down = f_down.getDataConst(SdomId((long)s));
+    for (int dim = 0; dim < 3 && mapped; ++dim) {
+      if (down[dim] < 0) continue;
+      const int r = pspace.globalSdomIdToRank(GlobalSdomId(down[dim]));
+      if (r == me) continue;
+      if (!peer_flags[r]) {
+        void *p = nullptr;
+        if (kb200_ipc_open(&flag_handles[64 * (size_t)r], &p) != 0) { mapped = 0; break; }
+        peer_flags[r] = (unsigned *)p;
+        px->m_opened.push_back(p);
+      }
+      const ExportEntry *found = nullptr;
+      for (int k = 0; k < head[2 * r + 1]; ++k) {
+        const ExportEntry &e = all[(size_t)r * mine.size() + k];
+        if (e.gid == down[dim] && e.dim == dim) { found = &e; break; }
+      }
+      void *p = nullptr;
+      if (!found || kb200_ipc_open(found->handle, &p) != 0) { mapped = 0; break; }
+      px->m_opened.push_back(p);
+      px->m_out_ptr[3 * s + dim] = (double *)p;
+      const long peer_local = *pspace.globalSdomIdToSdomId(GlobalSdomId(down[dim]));
+      px->m_out_flag[3 * s + dim] = peer_flags[r] + 3 * peer_local + dim;
+    }
+  }
+  // every rank must take the same path
+  std::vector<int> votes((size_t)nranks);
+  KB200_CALL(kb200_comm_allgather(&mapped, sizeof(int), votes.data()));
+  bool all_mapped = true;
+  for (int v : votes) all_mapped = all_mapped && v != 0;
+  px->m_usable = all_mapped;
+  if (!all_mapped) {
+    std::fill(px->m_out_ptr.begin(), px->m_out_ptr.end(), nullptr);
+    if (me == 0) fprintf(stderr, "kripke_b200: peer mapping unavailable (%s), faces go through NCCL send/recv\n", kb200_last_error());
+  }
+  return px;
+}
+
+PeerExchange::~PeerExchange() {
+  kb200_device_sync();
+  for (void *p : m_opened) kb200_ipc_close(p);
+  if (m_flags) kb200_free(m_flags);
+}
+
+void PeerExchange::signal(std::vector<SdomId> const &produced) {
+  std::vector<unsigned *> flags;
+  for (SdomId s : produced)
+    for (int dim = 0; dim < 3; ++dim)
+      if (m_out_flag[3 * (size_t)*s + dim]) flags.push_back(m_out_flag[3 * (size_t)*s + dim]);
+  if (!flags.empty()) KB200_CALL(kb200_p2p_signal(flags.data(), (int)flags.size(), m_epoch, nullptr));
+}
+
+void PeerExchange::wait(std::vector<SdomId> const &needed) {
+  std::vector<const unsigned *> flags;
+  for (SdomId s : needed)
+    for (int dim = 0; dim < 3; ++dim)
+      if (m_in_offrank[3 * (size_t)*s + dim]) flags.push_back(m_flags + 3 * (size_t)*s + dim);
+  if (!flags.empty()) KB200_CALL(kb200_p2p_wait(flags.data(), (int)flags.size(), m_epoch, nullptr));
+}
+
 // ---- ParallelComm base (src/Kripke/ParallelComm.cpp) -------------------------------------------------
 ParallelComm::ParallelComm(DataStore &data_store) : m_data_store(&data_store) {
   m_plane_data[0] = &m_data_store->getVariable<Field_IPlane>("i_plane");
@@ -152,6 +282,26 @@ void exchangeStage(DataStore &ds, FieldStorage<double> *planes[3], StageState co
   if (comm.size() <= 1) return;
   auto &f_up = ds.getVariable<Field_Adjacency>("upwind");
   auto &f_down = ds.getVariable<Field_Adjacency>("downwind");
+  PeerExchange *px = PeerExchange::get(ds);
+  if (px->usable()) {
+    // the sweep kernels of `stage` have stored their off-rank faces straight into the peers' plane chunks: raise the
+    // peers' flags behind them, and hold the stream until the faces stage+1 needs have been flagged by their producers
+    std::vector<SdomId> produced, needed;
+    for (size_t s = 0; s < st.depth.size(); ++s) {
+      SdomId sdom((long)s);
+      if (st.depth[s] == stage) produced.push_back(sdom);
+      else if (st.depth[s] == stage + 1) {
+        const long *up = f_up.getDataConst(sdom);
+        for (int dim = 0; dim < 3; ++dim)
+          if (up[dim] >= 0 && pspace.globalSdomIdToRank(GlobalSdomId(up[dim])) != (int)comm.rank())
+            planes[dim]->devicePtrOverwrite(sdom);  // defined by the peer: neither a pending zero-fill nor stale
+        needed.push_back(sdom);
+      }
+    }
+    px->signal(produced);
+    px->wait(needed);
+    return;
+  }
   auto &l2g = ds.getVariable<Field_SdomId2GlobalSdomId>("SdomId2GlobalSdomId");
   const long *local_to_global = l2g.getDataConst(SdomId(0));
   std::vector<Message> msgs;
@@ -187,8 +337,15 @@ SweepComm::SweepComm(DataStore &data_store) : ParallelComm(data_store) {
   st.depth.resize(n);
   for (size_t s = 0; s < n; ++s) st.depth[s] = sweepDepth(data_store, pspace, SdomId((long)s));
   g_stage[this] = st;
+  Comm comm;
+  if (comm.size() > 1) PeerExchange::get(data_store)->beginSweep();  // collective on first use; a new epoch of flags
 }
-SweepComm::~SweepComm() { g_stage.erase(this); }
+SweepComm::~SweepComm() {
+  g_stage.erase(this);
+  Comm comm;
+  // a peer may start the next sweep (and overwrite a plane chunk on this GPU) only when every rank is done reading
+  if (comm.size() > 1 && PeerExchange::get(*m_data_store)->usable()) KB200_CALL(kb200_comm_barrier(nullptr));
+}
 
 void SweepComm::addSubdomain(DataStore &data_store, SdomId sdom_id) { postRecvs(data_store, sdom_id); }
 
