@@ -224,6 +224,28 @@ int kb200_ipc_close(void *d_peer_ptr);
 int kb200_p2p_signal(unsigned *const *h_flags, int n, unsigned value, kb200_stream_t stream);
 int kb200_p2p_wait(const unsigned *const *h_flags, int n, unsigned value, kb200_stream_t stream);
 
+/* ---- problem generator on the device: the zone loops of Kripke::generateProblem that take seconds on the host at 128^3
+ *      zones (src/Kripke/Generate/Space.cpp:189-363).  Bit-identical to the host generator.
+ * kb200_generate_mix_count: material volume fractions of every zone by ns^3 sub-samples (d_frac [Zs][3]), materials per
+ *   zone (d_z2n = zone_to_num_mixelem), their exclusive prefix sum (d_z2m = zone_to_mixelem), the number of mixelems and
+ *   the three material volumes of this zone set (host outputs; synchronises the stream).
+ * kb200_generate_mix_fill: mixelem_to_zone / _material / _fraction in zone order, materials ascending inside a zone.
+ * kb200_generate_sigt: sigt_zonal(g,z) = sum over the zone's mixelems of fraction * sigt[material], stored in `layout`
+ *   order ([g][z] for DGZ, GDZ, GZD; [z][g] otherwise). */
+typedef struct {
+  int ni, nj, nk;                          /* zones of this zone set */
+  int i0, j0, k0;                          /* global index of its first zone */
+  double x_min, y_min, z_min, dx, dy, dz;  /* mesh origin and (uniform) zone widths */
+  int ns;                                  /* sub-samples per axis (InputVariables::num_material_subsamples) */
+} kb200_zoneset_desc;
+int kb200_generate_mix_count(const kb200_zoneset_desc *zs, double *d_frac, int *d_z2n, int *d_z2m, int *h_num_mixelem,
+                             double *h_material_volume3, kb200_stream_t stream);
+int kb200_generate_mix_fill(int Zs, const double *d_frac, const int *d_z2m, int *d_m2z, int *d_m2m, double *d_m2f,
+                            kb200_stream_t stream);
+int kb200_generate_sigt(int layout, int Gs, int Zs, const int *d_z2m, const int *d_z2n, const int *d_m2m, const double *d_m2f,
+                        const double *h_sigt3, double *d_sigt, kb200_stream_t stream);
+int kb200_device_bound(void);  /* 1 once kb200_init has bound this process to a GPU */
+
 /* ---- micro-benchmarks used for the roofline denominators (bench.py / tools) ------------------ */
 int kb200_peak_fp64_gflops(int use_dmma, int iters, double *gflops); /* DFMA / DMMA issue peak */
 int kb200_peak_copy_gbs(size_t bytes, int iters, double *gbs);       /* STREAM-style copy */

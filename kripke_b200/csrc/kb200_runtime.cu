@@ -410,6 +410,7 @@ int kb200_stream_destroy(kb200_stream_t s) {
   }
   return 0;
 }
+int kb200_device_bound(void) { return g_device >= 0 ? 1 : 0; }
 int kb200_memset(void *p, int byte_value, size_t bytes, kb200_stream_t s) {
   if (!bytes) return 0;
   KB_CUDA(cudaMemsetAsync(p, byte_value, bytes, resolve_stream(s)));

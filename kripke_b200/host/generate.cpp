@@ -323,11 +323,59 @@ void Kripke::Generate::generateSpace(DataStore &data_store, InputVariables const
   auto &f_volume = createField<Field_Zone2Double>(data_store, "volume", al_v, set_zone_linear);
   fillField(f_volume, zone_volume);
 
-  // sub-sample every zone to get its material volume fractions
+  double total_volume[3] = {0.0, 0.0, 0.0};
   const int ns = in.num_material_subsamples;
+  auto sdom_list = set_zone.getWorkList();
+  // With a GPU bound to the process the zone loops run there (csrc/kb200_generate.cu, bit-identical
+  // tables); without one -- planning runs, the CPU tests against the oracle -- the host loops below do the same work.
+  const bool on_device = kb200_device_bound() != 0 && !(getenv("KB200_HOST_GENERATOR") && getenv("KB200_HOST_GENERATOR")[0] == '1');
+  if (on_device) {
+    std::vector<size_t> sdom_to_num_mixed;
+    std::vector<double *> fracs;
+    auto &f_z2n = createField<Field_Zone2Int>(data_store, "zone_to_num_mixelem", al_v, set_zone_linear);
+    auto &f_z2m = createField<Field_Zone2MixElem>(data_store, "zone_to_mixelem", al_v, set_zone_linear);
+    for (SdomId s : sdom_list) {
+      kb200_zoneset_desc zs;
+      zs.ni = (int)set_zonei.size(s); zs.nj = (int)set_zonej.size(s); zs.nk = (int)set_zonek.size(s);
+      zs.i0 = (int)set_zonei.lower(s); zs.j0 = (int)set_zonej.lower(s); zs.k0 = (int)set_zonek.lower(s);
+      zs.x_min = x_min; zs.y_min = y_min; zs.z_min = z_min; zs.dx = dx; zs.dy = dy; zs.dz = dz; zs.ns = ns;
+      double *d_frac = nullptr;
+      KB200_CALL(kb200_alloc(3 * set_zone.size(s) * sizeof(double), (void **)&d_frac));
+      int nmix = 0;
+      double vol[3];
+      KB200_CALL(kb200_generate_mix_count(&zs, d_frac, f_z2n.devicePtrOverwrite(s), f_z2m.devicePtrOverwrite(s), &nmix, vol, nullptr));
+      for (int m = 0; m < 3; ++m) total_volume[m] += vol[m];
+      sdom_to_num_mixed.push_back((size_t)nmix);
+      fracs.push_back(d_frac);
+    }
+    auto &set_mixelem = data_store.newVariable<RangeSet>("Set/MixElem", pspace, SPACE_R, sdom_to_num_mixed);
+    auto &f_m2z = createField<Field_MixElem2Zone>(data_store, "mixelem_to_zone", al_v, set_mixelem);
+    auto &f_m2m = createField<Field_MixElem2Material>(data_store, "mixelem_to_material", al_v, set_mixelem);
+    auto &f_m2f = createField<Field_MixElem2Double>(data_store, "mixelem_to_fraction", al_v, set_mixelem);
+    for (size_t idx = 0; idx < sdom_list.size(); ++idx) {
+      SdomId s = sdom_list[idx];
+      KB200_CALL(kb200_generate_mix_fill((int)set_zone.size(s), fracs[idx], f_z2m.devicePtrConst(s), f_m2z.devicePtrOverwrite(s),
+                                         f_m2m.devicePtrOverwrite(s), f_m2f.devicePtrOverwrite(s), nullptr));
+    }
+    KB200_CALL(kb200_stream_sync(nullptr));
+    for (double *p : fracs) KB200_CALL(kb200_free(p));
+    Comm default_comm;
+    pspace.getComm(SPACE_R).allReduceSumDouble(total_volume, 3);
+    if (default_comm.rank() == 0)
+      printf("\n  Material Volumes=[%e, %e, %e]\n", total_volume[0], total_volume[1], total_volume[2]);
+    auto &set_group = data_store.getVariable<Set>("Set/Group");
+    auto &set_sigt = data_store.newVariable<ProductSet<2>>("Set/SigmaTZonal", pspace, SPACE_PR, set_group, set_zone);
+    auto &f_sigt = createField<Field_SigmaTZonal>(data_store, "sigt_zonal", al_v, set_sigt);
+    for (SdomId s : f_sigt.getWorkList())
+      KB200_CALL(kb200_generate_sigt((int)al_v.layout_v, (int)set_group.size(s), (int)set_zone.size(s), f_z2m.devicePtrConst(s),
+                                     f_z2n.devicePtrConst(s), f_m2m.devicePtrConst(s), f_m2f.devicePtrConst(s), in.sigt,
+                                     f_sigt.devicePtrOverwrite(s), nullptr));
+    return;
+  }
+
+  // sub-sample every zone to get its material volume fractions
   const double sample_vol_frac = 1.0 / (double)(ns * ns * ns);
   struct Mix { double fraction[3]; };
-  auto sdom_list = set_zone.getWorkList();
   std::vector<std::vector<Mix>> mix;
   std::vector<size_t> sdom_to_num_mixed;
   for (SdomId s : sdom_list) {
@@ -363,7 +411,6 @@ void Kripke::Generate::generateSpace(DataStore &data_store, InputVariables const
   auto &f_z2n = createField<Field_Zone2Int>(data_store, "zone_to_num_mixelem", al_v, set_zone_linear);
   auto &f_z2m = createField<Field_Zone2MixElem>(data_store, "zone_to_mixelem", al_v, set_zone_linear);
 
-  double total_volume[3] = {0.0, 0.0, 0.0};
   for (size_t idx = 0; idx < sdom_list.size(); ++idx) {
     SdomId s = sdom_list[idx];
     const int num_zones = (int)set_zone.size(s);
