@@ -118,6 +118,10 @@ typedef struct {
   const double *mixelem_to_fraction;        /* [num_mixelem] */
 } kb200_scattering_desc;
 int kb200_scattering(const kb200_scattering_desc *h_descs, int n, kb200_stream_t stream);
+/* The same with Kernel::source (Kernel/Source.cpp:59-75) folded into the epilogue of the tensor-core kernel: moment 0 also
+ * receives strength * (volume fraction of material 0 in the zone).  *folded = 1: done, kb200_source must not follow;
+ * *folded = 0: the kernel in use cannot fold (bit-exact mode, odd shapes) and only the scattering was done. */
+int kb200_scattering_source(const kb200_scattering_desc *h_descs, int n, double strength, int *folded, kb200_stream_t stream);
 
 /* ---- Source: Kripke::Kernel::source (src/Kripke/Kernel/Source.cpp:83-115, body :59-75) ----
  * phi_out(0,g,zone(mix)) += strength * fraction(mix) for every mixelem of material 0.

@@ -25,6 +25,7 @@ struct ScatGeom {
   int KC, nst;             // slab rows, slabs per tile
   long long in_b, in_r;    // moment (batch) stride, group (row) stride of phi / phi_out
   int ntn;                 // zone tiles
+  double source;           // != 0: Kernel::source folded in -- moment 0 also receives source * (volume fraction of material 0)
 };
 
 __device__ __forceinline__ void sc_cp_async16_zfill(void *smem_dst, const void *gsrc, bool valid) {
@@ -213,6 +214,11 @@ __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scatter
             const int n = ncol + 8 * nb;
             if (n < gm.Zs) {
               double2 v = make_double2(acc[a][nb][0], acc[a][nb][1]);
+              if (gm.source != 0.0 && b == 0) {  // Kernel/Source.cpp:59-75: phi_out(0,g,z) += strength * fraction of material 0
+                const double *f0 = fractions + (size_t)blockIdx.y * 3 * gm.Zs + n;
+                v.x = fma(gm.source, __ldg(f0), v.x);
+                v.y = fma(gm.source, __ldg(f0 + 1), v.y);
+              }
               double2 *p = reinterpret_cast<double2 *>(row + n);
               if (gm.accumulate) { const double2 old = *p; v.x += old.x; v.y += old.y; }
               *p = v;
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scatter
 using namespace kb200;
 
 // Returns 0 if handled, -1 if this path does not apply (caller falls back to the DFMA kernel), >0 on error.
-int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_descs, int sigs_layout, cudaStream_t st) {
+int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_descs, int sigs_layout, double source, cudaStream_t st) {
   const int layout = h[0].layout;
   if (layout != 0 && layout != 2) return -1;
   const char *env = getenv("KB200_SCATTER_DFMA");
@@ -252,6 +258,7 @@ int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_d
   memset(&gm, 0, sizeof(gm));
   gm.layout = layout; gm.sigs_layout = sigs_layout >= 0 ? sigs_layout : layout; gm.M = h[0].M; gm.L1 = h[0].L1; gm.G = h[0].G; gm.Gs = h[0].Gs; gm.Zs = h[0].Zs;
   gm.nsrc = h[0].nsrc; gm.accumulate = h[0].accumulate;
+  gm.source = source;
   gm.O = gm.Gs; gm.K = gm.nsrc * gm.Gs; gm.nkc4 = (gm.K + 3) / 4;
   const int Kp = gm.nkc4 * 4;
   gm.KC = Kp < 16 ? Kp : 16;

@@ -278,12 +278,24 @@ __global__ void __launch_bounds__(256) layout_transform_tiled_kernel(int nf, int
 
 using namespace kb200;
 
-int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_descs, int sigs_layout, cudaStream_t st);  // kb200_scatter_mma.cu
-int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, cudaStream_t st);  // kb200_scatter_row.cu
+int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_descs, int sigs_layout, double source, cudaStream_t st);  // kb200_scatter_mma.cu
+int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, double source, cudaStream_t st);  // kb200_scatter_row.cu
 
 extern "C" {
 
+static int scattering_impl(const kb200_scattering_desc *h, int n, double source, int *folded, kb200_stream_t stream);
 int kb200_scattering(const kb200_scattering_desc *h, int n, kb200_stream_t stream) {
+  return scattering_impl(h, n, 0.0, nullptr, stream);
+}
+// Scattering with Kernel::source folded into its epilogue where the kernel in use supports it: *folded = 1
+// means phi_out(0,g,z) has also received strength * (volume fraction of material 0 in zone z) and kb200_source must NOT be
+// called; *folded = 0 means only the scattering was done.
+int kb200_scattering_source(const kb200_scattering_desc *h, int n, double strength, int *folded, kb200_stream_t stream) {
+  KB_REQUIRE(folded, "kb200_scattering_source: null argument");
+  return scattering_impl(h, n, strength, folded, stream);
+}
+static int scattering_impl(const kb200_scattering_desc *h, int n, double source, int *folded, kb200_stream_t stream) {
+  if (folded) *folded = 0;
   if (n <= 0) return 0;
   KB_REQUIRE(h, "kb200_scattering: null descriptors");
   for (int i = 0; i < n; ++i) {
@@ -300,10 +312,10 @@ int kb200_scattering(const kb200_scattering_desc *h, int n, kb200_stream_t strea
   int rc = device_descs(h, sizeof(*h) * n, &d, st);
   if (rc) return rc;
   if (!exact_mode()) {  // default arithmetic: fp64 tensor-core path for the zone-fastest layouts
-    rc = kb200_scatter_mma_try(h, n, d, -1, st);
-    if (rc >= 0) return rc;
-    rc = kb200_scatter_row_try(h, n, st);  // moment-fastest layouts: transposed through the zone-fastest kernel
-    if (rc >= 0) return rc;
+    rc = kb200_scatter_mma_try(h, n, d, -1, source, st);
+    if (rc >= 0) { if (folded && rc == 0 && source != 0.0) *folded = 1; return rc; }
+    rc = kb200_scatter_row_try(h, n, source, st);  // moment-fastest layouts: transposed through the zone-fastest kernel
+    if (rc >= 0) { if (folded && rc == 0 && source != 0.0) *folded = 1; return rc; }
   }
   constexpr int GT = 8;
   long long total = (long long)h[0].M * h[0].Zs;

@@ -64,7 +64,8 @@ static RowScratch g_row_scratch;
 
 static int row_scratch(size_t count, size_t bytes_each, std::vector<double *> &out) {
   RowScratch &rs = g_row_scratch;
-  if (rs.bytes_each < bytes_each) {
+  // too small, or sized for a much bigger problem of the past (many small chunks must not each claim a huge buffer)
+  if (rs.bytes_each < bytes_each || rs.bytes_each > 2 * bytes_each) {
     if (!rs.bufs.empty()) KB_CUDA(cudaDeviceSynchronize());
     for (double *p : rs.bufs) cudaFree(p);
     rs.bufs.clear();
@@ -83,10 +84,10 @@ static int row_scratch(size_t count, size_t bytes_each, std::vector<double *> &o
 
 using namespace kb200;
 
-int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_descs, int sigs_layout, cudaStream_t st);  // kb200_scatter_mma.cu
+int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_descs, int sigs_layout, double source, cudaStream_t st);  // kb200_scatter_mma.cu
 
 // Returns 0 if handled, -1 if this path does not apply (caller falls back to the DFMA kernel), >0 on error.
-int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, cudaStream_t st) {
+int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, double source, cudaStream_t st) {
   const int layout = h[0].layout;
   if (layout != 1 && layout != 3 && layout != 4 && layout != 5) return -1;
   // The tiled generic layout transform is the faster transposer (measured 5.2 against 5.9-7.1 ms per scattering call)
@@ -133,7 +134,7 @@ int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, cudaStream_t st
   const void *d = nullptr;
   rc = device_descs(t.data(), sizeof(kb200_scattering_desc) * n, &d, st);
   if (rc) return rc;
-  rc = kb200_scatter_mma_try(t.data(), n, d, layout, st);
+  rc = kb200_scatter_mma_try(t.data(), n, d, layout, source, st);
   if (rc != 0) return rc < 0 ? -1 : rc;
   for (int i = 0; i < n; ++i) {
     if (generic) {

@@ -35,7 +35,9 @@
 // When pop_partial is non-null the kernel also accumulates Kernel::population's sum
 // (w(d)*psi)*volume(z) (src/Kripke/Kernel/Population.cpp:49-63) while psi is still in registers.
 #include "kb200_common.cuh"
+#include <cuda.h>
 #include <type_traits>
+#include <vector>
 
 namespace kb200 {
 
@@ -85,6 +87,16 @@ __device__ __forceinline__ void ir_bulk_g2s(unsigned smem_dst, const void *gsrc,
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
 }
+// TMA tensor copy global -> shared of one box of a 2-D tensor map (rows of 16 doubles, 128-byte swizzle): coordinates are
+// (element inside the 128-byte row = 0, row index)
+__device__ __forceinline__ void ir_tensor_g2s(unsigned smem_dst, const void *tmap, unsigned row, unsigned mbar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_dst), "l"(tmap), "r"(0u), "r"(row), "r"(mbar) : "memory");
+}
+// 128-byte swizzle of the staging slots filled through a tensor map: the 16-byte chunk index (address bits 4-6) is XORed
+// with the 128-byte row index (bits 7-9).  A lane's two 16-byte pieces sit 32 bytes apart from its neighbours', which
+// without the swizzle is a 2-way bank conflict on every ld.shared.v2.f64 of the row.
+__device__ __forceinline__ unsigned ir_swz(unsigned a) { return a ^ ((a >> 3) & 0x70u); }
 __device__ __forceinline__ void ir_mb_expect_tx(unsigned addr, unsigned bytes) {
   asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(addr), "r"(bytes) : "memory");
 }
@@ -149,9 +161,11 @@ __device__ __forceinline__ IItem irow_item(const IGeom &gm, int gi, int t, int w
 // TWO rows: half as many copy/mbarrier sequences per zone, two staging slots of a row pair each.
 // POPM: 0 = no population sum, 1 = (w*psi)*volume(z) with the zone volumes staged per row, 2 = every zone has the volume
 // `volc` (what Kripke's generator produces): the rows are summed first and scaled by w(d)*volc once per item
-template <int LR, bool FWD, bool UNI, int POPM, bool PAIR>
+// SWZ (PAIR only): rhs and sigt row pairs come in through tensor maps with the 128-byte swizzle (tm_rhs / tm_sigt)
+template <int LR, bool FWD, bool UNI, int POPM, bool PAIR, bool SWZ>
 __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGeom &gm, const IShared &sh,
-                                           const double *__restrict__ wq, const double *__restrict__ vol, const double volc) {
+                                           const double *__restrict__ wq, const double *__restrict__ vol, const double volc,
+                                           const void *tm_rhs, const void *tm_sigt) {
   constexpr bool POP = POPM == 1;  // the staged-volume machinery
   constexpr int R = IROW_RING, PD = IROW_PD, NS = PAIR ? 2 : IROW_NS;
   constexpr unsigned RB = PAIR ? 2048u : 1024u;  // bytes of the row block(s) of a warp's ER segments in one slot
@@ -226,8 +240,13 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
     if (ls == 0) {
       const unsigned roff = (unsigned)(((jd > 0) ? 2 * pp : 2 * pp + 1) * jstep);  // the lower of the two rows in memory
       const unsigned dst = stage0 + sqn * SB + (unsigned)seg * 2u * rowb;
-      ir_bulk_g2s(dst, ds.rhs + (it.off0 + roff), 2u * rowb, bar);
-      if (!gm.sig1 || lane == 0) ir_bulk_g2s(dst + RB, ds.sigt + (it.soff0 + roff), 2u * rowb, bar);
+      if (SWZ) {
+        ir_tensor_g2s(dst, tm_rhs, (it.off0 + roff) >> 4, bar);
+        if (!gm.sig1 || lane == 0) ir_tensor_g2s(dst + RB, tm_sigt, (it.soff0 + roff) >> 4, bar);
+      } else {
+        ir_bulk_g2s(dst, ds.rhs + (it.off0 + roff), 2u * rowb, bar);
+        if (!gm.sig1 || lane == 0) ir_bulk_g2s(dst + RB, ds.sigt + (it.soff0 + roff), 2u * rowb, bar);
+      }
       if (kload) ir_bulk_g2s(kin0 + sqn * RB + (unsigned)seg * 2u * rowb, ds.k_plane + (it.kpx0 + roff), 2u * rowb, bar);
       if (POP && lane == 0) ir_bulk_g2s(stage0 + sqn * SB + gm.vol_off, vol + (it.soff0 - (unsigned)it.g * gm.Zs + roff), 2u * rowb, bar);
     }
@@ -315,9 +334,9 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
       const double cy = tyc * sh.rdy[jz];
       {
         const unsigned sgo = (PAIR && gm.sig1) ? st - (unsigned)seg * 2u * rowb : st;  // shared rows: segment 0's block
-        const double2 e = ir_lds128(sgo + RB), f = ir_lds128(sgo + RB + 16);
+        const double2 e = ir_lds128(SWZ ? ir_swz(sgo + RB) : sgo + RB), f = ir_lds128(SWZ ? ir_swz(sgo + RB + 16) : sgo + RB + 16);
         const double s4[4] = {e.x, e.y, f.x, f.y};
-        const double2 a = ir_lds128(st), b = ir_lds128(st + 16);
+        const double2 a = ir_lds128(SWZ ? ir_swz(st) : st), b = ir_lds128(SWZ ? ir_swz(st + 16) : st + 16);
         r4[0] = a.x; r4[1] = a.y; r4[2] = b.x; r4[3] = b.y;
         const double csum = __dadd_rn(__dadd_rn(cx, cy), cz);
 #pragma unroll
@@ -466,14 +485,15 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
   return pop;
 }
 
-template <int LR, int POPM, bool PAIR>
+template <int LR, int POPM, bool PAIR, bool SWZ>
 __global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sweep_desc *__restrict__ descs, const __grid_constant__ IGeom gm,
                                                              const double *const *__restrict__ pop_w,
                                                              const double *const *__restrict__ pop_vol,
                                                              const double *__restrict__ pop_vol_const,
-                                                             double *__restrict__ pop_partial) {
+                                                             double *__restrict__ pop_partial,
+                                                             const CUtensorMap *__restrict__ tmaps) {
   constexpr bool POP = POPM != 0;
-  extern __shared__ __align__(16) unsigned char ism[];
+  extern __shared__ __align__(1024) unsigned char ism[];
   __shared__ kb200_sweep_desc ds;  // the descriptor is read all the time: keep it one LDS away (measured: faster than
   // passing the descriptors by value and reading them through the constant bank)
   if (threadIdx.x < sizeof(kb200_sweep_desc) / sizeof(int))
@@ -482,6 +502,7 @@ __global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sw
   const int Ds = gm.Ds, nj = gm.nj, nk = gm.nk, NW = gm.NW;
   IShared sh;
   unsigned char *p = ism;
+  if (SWZ) p += (1024u - (ir_smem_addr(ism) & 1023u)) & 1023u;  // the swizzle pattern repeats every 1 KB of shared memory
   sh.fkx = ir_smem_addr(p); p += (size_t)IROW_RING * (NW + 1) * (PAIR ? 2048 : 1024);
   sh.kin = ir_smem_addr(p); p += (size_t)4 * 1024;
   sh.stage = ir_smem_addr(p); p += (size_t)NW * (PAIR ? 2 : IROW_NS) * gm.sb;
@@ -517,13 +538,15 @@ __global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sw
   const double *wq = POP ? pop_w[blockIdx.y] : nullptr;
   const double *vol = POPM == 1 ? pop_vol[blockIdx.y] : nullptr;
   const double volc = POPM == 2 ? pop_vol_const[blockIdx.y] : 0.0;
+  const void *tm_rhs = SWZ ? (const void *)(tmaps + 2 * blockIdx.y) : nullptr;
+  const void *tm_sigt = SWZ ? (const void *)(tmaps + 2 * blockIdx.y + 1) : nullptr;
   double pop;
   if (uniform_x) {
-    if (ds.id > 0) pop = irow_run<LR, true, true, POPM, PAIR>(ds, gm, sh, wq, vol, volc);
-    else pop = irow_run<LR, false, true, POPM, PAIR>(ds, gm, sh, wq, vol, volc);
+    if (ds.id > 0) pop = irow_run<LR, true, true, POPM, PAIR, SWZ>(ds, gm, sh, wq, vol, volc, tm_rhs, tm_sigt);
+    else pop = irow_run<LR, false, true, POPM, PAIR, SWZ>(ds, gm, sh, wq, vol, volc, tm_rhs, tm_sigt);
   } else {
-    if (ds.id > 0) pop = irow_run<LR, true, false, POPM, PAIR>(ds, gm, sh, wq, vol, volc);
-    else pop = irow_run<LR, false, false, POPM, PAIR>(ds, gm, sh, wq, vol, volc);
+    if (ds.id > 0) pop = irow_run<LR, true, false, POPM, PAIR, SWZ>(ds, gm, sh, wq, vol, volc, tm_rhs, tm_sigt);
+    else pop = irow_run<LR, false, false, POPM, PAIR, SWZ>(ds, gm, sh, wq, vol, volc, tm_rhs, tm_sigt);
   }
 
   if (POP) {  // fixed-order block reduction: lanes, then warps
@@ -542,24 +565,53 @@ __global__ void __launch_bounds__(IROW_MAXT, 1) sweep_irow_kernel(const kb200_sw
 
 using namespace kb200;
 
-template <int LR, bool PAIR>
+template <int LR, bool PAIR, bool SWZ>
 static int launch_irow(const kb200_sweep_desc *d_descs, int n, const IGeom &gm, int cps, size_t smem, const double *const *pw,
-                       const double *const *pv, const double *pvc, double *pp, cudaStream_t st) {
+                       const double *const *pv, const double *pvc, double *pp, const CUtensorMap *tm, cudaStream_t st) {
   dim3 grid(cps, n, 1);
   if (pp && pvc) {
-    auto k = sweep_irow_kernel<LR, 2, PAIR>;
+    auto k = sweep_irow_kernel<LR, 2, PAIR, SWZ>;
     KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, pw, pv, pvc, pp);
+    k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, pw, pv, pvc, pp, tm);
   } else if (pp) {
-    auto k = sweep_irow_kernel<LR, 1, PAIR>;
+    auto k = sweep_irow_kernel<LR, 1, PAIR, SWZ>;
     KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, pw, pv, nullptr, pp);
+    k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, pw, pv, nullptr, pp, tm);
   } else {
-    auto k = sweep_irow_kernel<LR, 0, PAIR>;
+    auto k = sweep_irow_kernel<LR, 0, PAIR, SWZ>;
     KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, nullptr, nullptr, nullptr, nullptr);
+    k<<<grid, gm.NW * 32, smem, st>>>(d_descs, gm, nullptr, nullptr, nullptr, nullptr, tm);
   }
   return post_launch("sweep_irow");
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+// a chunk of `count` doubles seen as rows of 16 doubles (128 bytes); one box = `box_rows` rows, 128-byte swizzle
+static bool irow_tensor_map(CUtensorMap *tm, const double *base, unsigned long long count, unsigned box_rows) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc || count % 16 != 0 || ((uintptr_t)base & 127) != 0) return false;
+  const cuuint64_t dims[2] = {16, count / 16};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {16, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Returns 0 if the batch was handled, -1 if this path does not apply (caller falls back), >0 on error.
@@ -610,13 +662,19 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
   bool pair = (nj % 2 == 0) && nj >= 4 && !(pe && pe[0] == '0');
   bool volu = d_pop_partial && h_pop_vol_const && d_pop_vol_const;
   for (int i = 0; volu && i < n; ++i) volu = h_pop_vol_const[i] > 0.0;
+  const char *se = getenv("KB200_IROW_SWIZZLE");
+  bool swz = false;
   size_t smem = 0;
   for (;;) {
     const unsigned rb = pair ? 2048u : 1024u;
     gm.vol_off = rb + ((pair && gm.sig1) ? 2u * rowb : rb);  // a shared sigt row pair takes 2*rowb instead of a full block
     gm.sb = gm.vol_off + ((d_pop_partial && !volu) ? (pair ? 2u : 1u) * rowb : 0u);
+    // swizzled staging (tensor maps): 1 KB row pairs per segment, every slot a multiple of 1 KB from a 1 KB aligned base
+    swz = pair && LR >= 16 && !(se && se[0] == '0') && encode_tiled() != nullptr;
+    if (swz) gm.sb = (gm.sb + 1023u) & ~1023u;
+    const size_t align_slack = swz ? 1024 : 0;
     smem = (size_t)IROW_RING * (gm.NW + 1) * rb + (size_t)4 * 1024 + (size_t)gm.NW * (pair ? 2 : IROW_NS) * gm.sb +
-           ((size_t)4 * gm.Ds + nj + nk + 32 + 2 * (gm.NW + 1) * IROW_RING + gm.NW * IROW_NS + 2) * sizeof(double);
+           ((size_t)4 * gm.Ds + nj + nk + 32 + 2 * (gm.NW + 1) * IROW_RING + gm.NW * IROW_NS + 2) * sizeof(double) + align_slack;
     if (smem <= 226 * 1024 || !pair) break;
     pair = false;
   }
@@ -635,15 +693,30 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
   if (pop_count) *pop_count = pp ? cps * n : 0;
   const kb200_sweep_desc *dd = (const kb200_sweep_desc *)d_descs;
   const double *pvc = (pp && volu) ? d_pop_vol_const : nullptr;
-#define IROW_LAUNCH(LR_) return pair ? launch_irow<LR_, true>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pvc, pp, st) \
-                                    : launch_irow<LR_, false>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pvc, pp, st)
+  // rows of at least 512 bytes, fetched as pairs: stage rhs and sigt through tensor maps with the 128-byte swizzle
+  const CUtensorMap *d_tm = nullptr;
+  if (swz) {
+    std::vector<CUtensorMap> tm(2 * (size_t)n);
+    const unsigned long long Zs = (unsigned long long)ni * nj * nk;
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i)
+      ok = irow_tensor_map(&tm[2 * i], h[i].rhs, (unsigned long long)gm.Ds * gm.Gs * Zs, 2u * rowb / 128u) &&
+           irow_tensor_map(&tm[2 * i + 1], h[i].sigt, (unsigned long long)gm.Gs * Zs, 2u * rowb / 128u);
+    const void *d = nullptr;
+    if (ok && device_descs(tm.data(), tm.size() * sizeof(CUtensorMap), &d, st) == 0) d_tm = (const CUtensorMap *)d;
+    KB_REQUIRE(d_tm, "sweep_irow: cannot build the tensor maps of the staged rows");
+  }
+#define IROW_LAUNCH(LR_) return pair ? launch_irow<LR_, true, false>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pvc, pp, nullptr, st) \
+                                    : launch_irow<LR_, false, false>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pvc, pp, nullptr, st)
+#define IROW_LAUNCH_SWZ(LR_) if (swz) return launch_irow<LR_, true, true>(dd, n, gm, cps, smem, d_pop_w, d_pop_vol, pvc, pp, d_tm, st)
   switch (LR) {
     case 1: IROW_LAUNCH(1);
     case 2: IROW_LAUNCH(2);
     case 4: IROW_LAUNCH(4);
     case 8: IROW_LAUNCH(8);
-    case 16: IROW_LAUNCH(16);
-    default: IROW_LAUNCH(32);
+    case 16: IROW_LAUNCH_SWZ(16); IROW_LAUNCH(16);
+    default: IROW_LAUNCH_SWZ(32); IROW_LAUNCH(32);
   }
 #undef IROW_LAUNCH
+#undef IROW_LAUNCH_SWZ
 }

@@ -48,6 +48,7 @@ struct PGeom {  // kernel parameter: lives in the constant bank, costs no regist
   int nslices, nitems, nctas;     // items = (subdomain, tile of the diagonal, slice), cut into nctas contiguous runs
   int j_tiles, k_tiles;
   int d_fast;                     // d is the faster of the two element indices
+  int exp;                        // timing experiments (KB200_PENCIL_EXP bitmask; results are wrong when non-zero)
   unsigned fa, fg, fz;            // psi/rhs strides: direction, group, zone
   unsigned sg, sz;                // sigt strides: group, zone
   unsigned ipd, ipg, ipa, ipb, jpd, jpg, jpa, jpb, kpd, kpg, kpa, kpb;  // plane strides (strides_plane)
@@ -69,6 +70,8 @@ __device__ __forceinline__ double p_ldg(const double *p) {  // streamed once: do
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+// (measured dead end: an L2 evict-first policy on the rhs loads and psi stores, meant to keep sigt and the face planes in
+// L2, made the kernel slower -- 15.8 -> 16.7 ms in ZGD)
 __device__ __forceinline__ double p_ld_cg(const double *p) {  // faces written by other CTAs / earlier launches: L2
   double v;
   asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
@@ -99,7 +102,8 @@ constexpr unsigned OK = OJ + PR * PK * 256;                 // [PR][PJ][32] doub
 constexpr unsigned OB = OK + PR * PJ * 256;                 // [2][PK + PJ][32] doubles: tile-boundary faces entering it
 constexpr unsigned OC = OB + 2 * (PK + PJ) * 256;           // [2 + PJ + PK][32] doubles: 2*cos/delta of every lane's direction
 constexpr unsigned OP = OC + (2 + PJ + PK) * 256;           // [4][32] 8-byte slots: i/j/k plane element offset, direction
-constexpr unsigned OT = OP + 4 * 256;                       // PTile
+constexpr unsigned OS = OP + 4 * 256;                       // [32] doubles: running population sum of every lane
+constexpr unsigned OT = OS + 256;                           // PTile
 constexpr unsigned OM = OT + ((sizeof(PTile) + 255) / 256) * 256;  // mbarriers: full_j[PR], full_k[PR], empty_j[PR], empty_k[PR]
 constexpr unsigned OMFJ = OM, OMFK = OM + 8 * PR, OMEJ = OM + 16 * PR, OMEK = OM + 24 * PR;
 constexpr unsigned WBSZ = OM + 256;
@@ -155,7 +159,8 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
   unsigned b = 0, sb = 0;   // psi/rhs and sigt element offset of this lane at the current zone column (without the line part)
   unsigned iz = 0;          // memory i index of the current step
   int i = 0;
-  double pop = 0.0, acc = 0.0;
+  double acc = 0.0;         // population: sum of psi (x volume) over the current slice; the total lives in shared memory
+  if (POP) p_sts(mb + OS, 0.0);
   double R[PL], S[PL], FI[PL];
 #pragma unroll
   for (int l = 0; l < PL; ++l) { R[l] = 0.0; S[l] = 1.0; FI[l] = 0.0; zrow[l] = 0u; }
@@ -218,14 +223,14 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
         zrow[l] = (unsigned)((kz[kl] * gm.nj + jz[jl]) * ni);
       }
     fl = 0;
-    if ((tjn - 1) / PJ == J) fl |= F_JLAST;
-    if ((tkn - 1) / PK == K) fl |= F_KLAST;
+    if ((tjn - 1) / PJ == J && !(gm.exp & 2)) fl |= F_JLAST;
+    if ((tkn - 1) / PK == K && !(gm.exp & 2)) fl |= F_KLAST;
     if (J > 0) fl |= F_JRING;
     if (K > 0) fl |= F_KRING;
     if (J < PWJ - 1) fl |= F_JNEXT;
     if (K < PWK - 1) fl |= F_KNEXT;
-    if (J == 0 && !(tl.ds.inflow_zero[1] != 0 && tj == 0)) fl |= F_JB;
-    if (K == 0 && !(tl.ds.inflow_zero[2] != 0 && tk == 0)) fl |= F_KB;
+    if (J == 0 && !(tl.ds.inflow_zero[1] != 0 && tj == 0) && !(gm.exp & 1)) fl |= F_JB;
+    if (K == 0 && !(tl.ds.inflow_zero[2] != 0 && tk == 0) && !(gm.exp & 1)) fl |= F_KB;
     if (tj == gm.j_tiles - 1 && tl.ds.out_plane[1] != nullptr) fl |= F_JOUT;
     if (tk == gm.k_tiles - 1 && tl.ds.out_plane[2] != nullptr) fl |= F_KOUT;
     if (tl.ds.inflow_zero[0] != 0) fl |= F_IZERO;
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
     unsigned eoff, soff, ipo, jpo, kpo;
     int d;
     PTile &tl = TL;
-    fl = slice_elem(sl, eoff, soff, ipo, jpo, kpo, d) ? (fl | F_VALID) : (fl & ~F_VALID);
+    fl = (slice_elem(sl, eoff, soff, ipo, jpo, kpo, d) && !(gm.exp & 4)) ? (fl | F_VALID) : (fl & ~F_VALID);
     iz = (fl & F_FWD) ? 0u : (unsigned)(ni - 1);
     i = 0;
     b = eoff + iz * fz; sb = soff + iz * sz;
@@ -305,8 +310,9 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
 
   // one local step at global step H (even H read boundary slot 0 ... the slot alternates with the LOCAL step, see bsl)
   // FULL: every line of the pencil exists (no per-line tests, long basic blocks for the scheduler)
-  auto step = [&](auto full_tag, const int t, const unsigned bslot) {
+  auto step = [&](auto full_tag, auto volu_tag, const int t, const unsigned bslot) {
     constexpr bool FULL = decltype(full_tag)::value;
+    constexpr bool VOLU = decltype(volu_tag)::value;  // population: every zone has the same volume (no volume loads)
     const unsigned ws = (unsigned)t & (PR - 1), rs = ws;  // ring slot of this local step (same number on both sides)
     const unsigned ph = ((unsigned)t / PR) & 1u;           // phase parity of the slot's current use
     const bool last_i = (i == ni - 1);
@@ -389,7 +395,7 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
           if (valid) {
             psi_b[zrow[l] * fz + b] = p;
             if (POP) {
-              if (fl & F_VOLU) acc += p;
+              if (VOLU) acc += p;
               else acc = fma(p, __ldg(TL.vol + (zrow[l] + iz)), acc);
             }
           }
@@ -425,7 +431,7 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
           if (valid) {
             psi_b[zrow[l] * fz + b] = p;
             if (POP) {
-              if (fl & F_VOLU) acc += p;
+              if (VOLU) acc += p;
               else acc = fma(p, __ldg(TL.vol + (zrow[l] + iz)), acc);
             }
           }
@@ -495,7 +501,7 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
       if (POP) {
         if (valid) {
           const double vc = TL.vol_c;
-          pop = fma(pop_w[pair / gm.ntiles][p_lds32(mb + OP + 768)] * (vc > 0.0 ? vc : 1.0), acc, pop);
+          p_sts(mb + OS, fma(pop_w[pair / gm.ntiles][p_lds32(mb + OP + 768)] * (vc > 0.0 ? vc : 1.0), acc, p_lds(mb + OS)));
         }
         acc = 0.0;
       }
@@ -514,8 +520,13 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
   unsigned bslot = 0;  // boundary slot holding the current step's faces
 #pragma unroll 1
   for (int t = 0; t < T; ++t) {
-    if (lmask == (1u << PL) - 1u) bslot = step(std::true_type{}, t, bslot);
-    else if (lmask != 0u) bslot = step(std::false_type{}, t, bslot);
+    if (lmask == (1u << PL) - 1u) {
+      if (!POP || (fl & F_VOLU)) bslot = step(std::true_type{}, std::true_type{}, t, bslot);
+      else bslot = step(std::true_type{}, std::false_type{}, t, bslot);
+    } else if (lmask != 0u) {
+      if (!POP || (fl & F_VOLU)) bslot = step(std::false_type{}, std::true_type{}, t, bslot);
+      else bslot = step(std::false_type{}, std::false_type{}, t, bslot);
+    }
     else {  // a pencil outside a ragged tile: keep the hand-shakes and the item bookkeeping going
       const unsigned ws = (unsigned)t & (PR - 1), ph = ((unsigned)t / PR) & 1u, wb = mb - 8u * lane;
       if (fl & F_KRING) { p_mb_wait(wb - PWJ * WBSZ + OMFK + 8u * ws, ph); p_mb_arrive(wb - PWJ * WBSZ + OMEK + 8u * ws); }
@@ -538,7 +549,7 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
 
   if (POP) {  // fixed-order block reduction: lanes, then warps
     double *red = reinterpret_cast<double *>(psm + PW * WBSZ);
-    pop = warp_sum(pop);
+    double pop = warp_sum(p_lds(mb + OS));
     if (lane == 0) red[threadIdx.x >> 5] = pop;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -569,6 +580,7 @@ int kb200_sweep_pencil_try(const kb200_sweep_desc *h, int n, const void *d_descs
   memset(&gm, 0, sizeof(gm));
   gm.layout = layout; gm.Ds = h[0].Ds; gm.Gs = h[0].Gs; gm.ni = h[0].ni; gm.nj = h[0].nj; gm.nk = h[0].nk;
   if ((double)gm.Ds * gm.Gs * gm.ni * gm.nj * gm.nk >= 2147483648.0) return -1;  // 32-bit element offsets
+  { const char *x = getenv("KB200_PENCIL_EXP"); gm.exp = x ? atoi(x) : 0; }
   gm.j_tiles = (gm.nj + PTJ - 1) / PTJ;
   gm.k_tiles = (gm.nk + PTK - 1) / PTK;
   const int E = gm.Ds * gm.Gs;

@@ -24,11 +24,13 @@
 #define KRIPKE_VERSION "b200-0.1 (interface of Kripke 1.2.5-dev)"
 
 // src/Kripke.h:39-53
-#define KRIPKE_ABORT(...)      \
-  do {                         \
-    printf(__VA_ARGS__);       \
-    fflush(stdout);            \
-    exit(1);                   \
+#define KRIPKE_ABORT(...)       \
+  do {                          \
+    printf(__VA_ARGS__);        \
+    fflush(stdout);             \
+    fprintf(stderr, __VA_ARGS__); /* embedders (ctypes) may have redirected stdout */ \
+    fflush(stderr);             \
+    exit(1);                    \
   } while (0)
 #define KRIPKE_ASSERT(EXPR, ...)                        \
   do {                                                  \
@@ -548,7 +550,10 @@ namespace Kernel {
 void LPlusTimes(Core::DataStore &data_store);
 void LTimes(Core::DataStore &data_store);
 double population(Core::DataStore &data_store);
-void scattering(Core::DataStore &data_store);
+// fold_source: the caller promises that Kernel::source(data_store) is the next thing to touch phi_out (as in
+// SteadyStateSolver.cpp:59-65); the source term is then added by the scattering kernel's epilogue and that source call
+// only checks the promise
+void scattering(Core::DataStore &data_store, bool fold_source = false);
 void source(Core::DataStore &data_store);
 void sweepSubdomain(Core::DataStore &data_store, SdomId sdom_id);
 // batched form: all subdomains of the list must be mutually independent (used by SweepSolver)

@@ -110,8 +110,20 @@ void Kripke::Kernel::LPlusTimes(DataStore &data_store) {
 }
 
 // ---- scattering: src/Kripke/Kernel/Scattering.cpp:112-164 -------------------------------------------------
-void Kripke::Kernel::scattering(DataStore &data_store) {
+namespace {
+// Kernel::source folded into the scattering epilogue: the write epoch every phi_out chunk had right after a
+// scattering call that also added the source.  Kernel::source is a no-op for exactly that state of phi_out.
+struct SourceFold {
+  const void *field = nullptr;
+  std::vector<unsigned long> epochs;
+  bool valid = false;
+};
+SourceFold g_src_fold;
+}  // namespace
+
+void Kripke::Kernel::scattering(DataStore &data_store, bool fold_source) {
   KRIPKE_TIMER(data_store, Scattering);
+  g_src_fold.valid = false;
   auto &pspace = data_store.getVariable<PartitionSpace>("pspace");
   auto &set_group = data_store.getVariable<Set>("Set/Group");
   auto &set_moment = data_store.getVariable<Set>("Set/Moment");
@@ -156,6 +168,21 @@ void Kripke::Kernel::scattering(DataStore &data_store) {
     d.phi_out = d.accumulate ? field_phi_out.devicePtr(sdom_dst) : field_phi_out.devicePtrOverwrite(sdom_dst);
     (d.accumulate ? a : b).push_back(d);
   }
+  const char *nf = getenv("KB200_FOLD_SOURCE");
+  if (fold_source && !(nf && nf[0] == '0')) {
+    int fb = 1, fa = 1;
+    if (!b.empty()) KB200_CALL(kb200_scattering_source(b.data(), (int)b.size(), 1.0 /* Kernel/Source.cpp:98 */, &fb, nullptr));
+    if (!a.empty()) KB200_CALL(kb200_scattering_source(a.data(), (int)a.size(), 1.0, &fa, nullptr));
+    if (fb && fa) {
+      g_src_fold.field = &field_phi_out;
+      g_src_fold.epochs.clear();
+      for (auto sdom : field_phi_out.getWorkList()) g_src_fold.epochs.push_back(field_phi_out.writeEpoch(sdom));
+      g_src_fold.valid = true;
+    } else if (fb != fa) {
+      KRIPKE_ABORT("scattering: the source was folded into one batch of phi_out chunks but not the other\n");
+    }
+    return;
+  }
   if (!b.empty()) KB200_CALL(kb200_scattering(b.data(), (int)b.size(), nullptr));
   if (!a.empty()) KB200_CALL(kb200_scattering(a.data(), (int)a.size(), nullptr));
 }
@@ -163,6 +190,15 @@ void Kripke::Kernel::scattering(DataStore &data_store) {
 // ---- source: src/Kripke/Kernel/Source.cpp:83-115 ---------------------------------------------------------------
 void Kripke::Kernel::source(DataStore &data_store) {
   KRIPKE_TIMER(data_store, Source);
+  if (g_src_fold.valid && g_src_fold.field == &data_store.getVariable<Field_Moments>("phi_out")) {
+    auto &f = data_store.getVariable<Field_Moments>("phi_out");
+    bool same = true;
+    size_t k = 0;
+    for (auto sdom : f.getWorkList()) same = same && k < g_src_fold.epochs.size() && f.writeEpoch(sdom) == g_src_fold.epochs[k++];
+    g_src_fold.valid = false;
+    if (same) return;  // the scattering call that produced this phi_out has already added the source
+    KRIPKE_ABORT("source: phi_out changed between the scattering that folded the source in and this call\n");
+  }
   auto &set_group = data_store.getVariable<Set>("Set/Group");
   auto &set_mixelem = data_store.getVariable<Set>("Set/MixElem");
   auto &set_moment = data_store.getVariable<Set>("Set/Moment");

@@ -35,7 +35,7 @@ int Kripke::SteadyStateSolver(DataStore &data_store, size_t max_iter, bool block
     Kernel::LTimes(data_store);
 
     Kernel::kConst(data_store.getVariable<Field_Moments>("phi_out"), 0.0);
-    Kernel::scattering(data_store);
+    Kernel::scattering(data_store, true);  // Kernel::source below is folded into its epilogue
 
     Kernel::source(data_store);
 

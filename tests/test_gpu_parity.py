@@ -486,3 +486,21 @@ def test_device_generator_matches_host_generator_at_scale(gpu, monkeypatch):
     host = gpu.Problem(args)
     for n in GEN_ZONE_FIELDS:
         assert np.array_equal(dev.field(n), host.field(n)), n
+
+
+@pytest.mark.parametrize("layout", ["DGZ", "GDZ", "GZD", "ZGD"])
+def test_source_folded_into_scattering_matches_separate_kernels(gpu, monkeypatch, layout):
+    """SteadyStateSolver's scattering call adds Kernel::source's term in the epilogue of the tensor-core kernel
+    (Kernel/Source.cpp:59-75 touches only the moment-0 slab that kernel has just written).  One iteration through the
+    solver with and without the fold must leave bit-identical phi_out and rhs, and the same particle count."""
+    args = f"--zones 12,20,10 --groups 8 --quad 16 --legendre 2 --gset 2 --dset 8 --zset 1,2,1 --niter 2 --layout {layout}"
+    res = {}
+    for fold in ("1", "0"):
+        monkeypatch.setenv("KB200_FOLD_SOURCE", fold)
+        p = gpu.Problem(args)
+        parts = p.solve()
+        res[fold] = (parts, p.field("phi_out").copy(), p.field("rhs").copy())
+        p.close()
+    assert res["1"][0] == res["0"][0]
+    assert float(np.max(np.abs(res["1"][1]))) > 0.0
+    assert np.array_equal(res["1"][1], res["0"][1]) and np.array_equal(res["1"][2], res["0"][2])
