@@ -48,6 +48,9 @@ struct PGeom {  // kernel parameter: lives in the constant bank, costs no regist
   int nslices, nitems, nctas;     // items = (subdomain, tile of the diagonal, slice), cut into nctas contiguous runs
   int j_tiles, k_tiles;
   int d_fast;                     // d is the faster of the two element indices
+  int eps;                        // elements per slice (<= 32): lanes >= eps idle.  Where the elements of a zone are NOT one
+                                  // contiguous run (GZD: runs of Ds directions, DZG: runs of Gs groups) a slice holds whole runs,
+                                  // so that a warp's access is one contiguous piece instead of two pieces from different pages
   int exp;                        // timing experiments (KB200_PENCIL_EXP bitmask; results are wrong when non-zero)
   unsigned fa, fg, fz;            // psi/rhs strides: direction, group, zone
   unsigned sg, sz;                // sigt strides: group, zone
@@ -167,8 +170,8 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
 
   // element offsets of slice `sl` for this lane
   auto slice_elem = [&](int sl, unsigned &eoff, unsigned &soff, unsigned &ipo, unsigned &jpo, unsigned &kpo, int &d) {
-    int e = sl * 32 + lane;
-    const bool v = e < gm.Ds * gm.Gs;
+    int e = sl * gm.eps + min(lane, gm.eps - 1);  // idle lanes shadow the slice's last element: no extra sectors
+    const bool v = lane < gm.eps && e < gm.Ds * gm.Gs;
     e = min(e, gm.Ds * gm.Gs - 1);
     int g;
     if (gm.d_fast) { d = e % gm.Ds; g = e / gm.Ds; }
@@ -584,7 +587,13 @@ int kb200_sweep_pencil_try(const kb200_sweep_desc *h, int n, const void *d_descs
   gm.j_tiles = (gm.nj + PTJ - 1) / PTJ;
   gm.k_tiles = (gm.nk + PTK - 1) / PTK;
   const int E = gm.Ds * gm.Gs;
-  gm.nslices = (E + 31) / 32;
+  gm.eps = 32;
+  if (layout == 1 || layout == 3) {  // DZG: runs of Gs groups, GZD: runs of Ds directions
+    const int run = (layout == 3) ? gm.Ds : gm.Gs;
+    const char *ae = getenv("KB200_PENCIL_ALIGN");
+    if (run < 32 && !(ae && ae[0] == '0')) gm.eps = (32 / run) * run;
+  }
+  gm.nslices = (E + gm.eps - 1) / gm.eps;
   {
     const long long Zs = (long long)gm.ni * gm.nj * gm.nk;
     const Strides3 fs = strides_dgz(layout, gm.Ds, gm.Gs, Zs);

@@ -170,10 +170,12 @@ void Kripke::Kernel::scattering(DataStore &data_store, bool fold_source) {
   }
   const char *nf = getenv("KB200_FOLD_SOURCE");
   if (fold_source && !(nf && nf[0] == '0')) {
-    int fb = 1, fa = 1;
+    int fb = -1, fa = -1;  // -1: no such batch
     if (!b.empty()) KB200_CALL(kb200_scattering_source(b.data(), (int)b.size(), 1.0 /* Kernel/Source.cpp:98 */, &fb, nullptr));
     if (!a.empty()) KB200_CALL(kb200_scattering_source(a.data(), (int)a.size(), 1.0, &fa, nullptr));
-    if (fb && fa) {
+    if (fb == -1) fb = fa;
+    if (fa == -1) fa = fb;
+    if (fb == 1 && fa == 1) {
       g_src_fold.field = &field_phi_out;
       g_src_fold.epochs.clear();
       for (auto sdom : field_phi_out.getWorkList()) g_src_fold.epochs.push_back(field_phi_out.writeEpoch(sdom));
