@@ -51,6 +51,8 @@ struct PGeom {  // kernel parameter: lives in the constant bank, costs no regist
   int eps;                        // elements per slice (<= 32): lanes >= eps idle.  Where the elements of a zone are NOT one
                                   // contiguous run (GZD: runs of Ds directions, DZG: runs of Gs groups) a slice holds whole runs,
                                   // so that a warp's access is one contiguous piece instead of two pieces from different pages
+  int interleave;                 // items of a CTA: 0 = one contiguous run, 1 = every nctas-th item (neighbouring CTAs then work on
+                                  // neighbouring slices of the same zones at the same time: contiguous DRAM bursts)
   int exp;                        // timing experiments (KB200_PENCIL_EXP bitmask; results are wrong when non-zero)
   unsigned fa, fg, fz;            // psi/rhs strides: direction, group, zone
   unsigned sg, sz;                // sigt strides: group, zone
@@ -146,8 +148,12 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
   __syncthreads();
 
   // ---- this CTA's run of items ----
-  const int item_hi = (int)(((long long)(blockIdx.x + 1) * gm.nitems) / gm.nctas);
-  int item = (int)(((long long)blockIdx.x * gm.nitems) / gm.nctas);
+  // `item` counts this CTA's items; ITEM(k) is the k-th one's index in the launch's (subdomain, tile, slice) list
+  const int il = gm.interleave;
+  const int item_hi = il ? (gm.nitems - (int)blockIdx.x + gm.nctas - 1) / gm.nctas
+                         : (int)(((long long)(blockIdx.x + 1) * gm.nitems) / gm.nctas);
+  int item = il ? 0 : (int)(((long long)blockIdx.x * gm.nitems) / gm.nctas);
+#define ITEM(k) (il ? (int)blockIdx.x + (k) * gm.nctas : (k))
   const int T = (item_hi - item) * ni;               // local steps of every warp
   const unsigned fz = gm.fz, sz = gm.sz;
 
@@ -299,7 +305,8 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
     }
   };
   // start of an item that does not continue the previous one (first item, or the tile changed): everything from scratch
-  auto item_start = [&](int it) {
+  auto item_start = [&](int k) {
+    const int it = ITEM(k);
     const int pr = it / gm.nslices, sl = it - pr * gm.nslices;
     if (pr != pair) tile_setup(pr);
     slice_setup(sl);
@@ -329,9 +336,9 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
       if (fl & (F_JB | F_KB)) { njp = p_lds32(mb + OP + 256); nkp = p_lds32(mb + OP + 512); }
     } else {
       izn = fwd ? 0u : (unsigned)(ni - 1);
-      const int nit = item + 1;
+      const int nit = ITEM(item + 1);
       const int npr = nit / gm.nslices;
-      more = nit < item_hi && npr == pair;
+      more = item + 1 < item_hi && npr == pair;
       unsigned eo = 0, so = 0, ipo;
       int d;
       if (more) slice_elem(nit - npr * gm.nslices, eo, so, ipo, njp, nkp, d);
@@ -510,7 +517,7 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
       }
       ++item;
       if (item < item_hi) {
-        if (more) slice_setup(item - pair * gm.nslices);
+        if (more) slice_setup(ITEM(item) - pair * gm.nslices);
         else item_start(item);  // another tile or subdomain
       }
       return more ? (bslot ^ 1u) : 0u;
@@ -540,7 +547,7 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
         ++item;
         i = 0;
         if (item < item_hi) {
-          const int pr = item / gm.nslices;
+          const int pr = ITEM(item) / gm.nslices;
           if (pr != pair) { item_start(item); bslot = 0; }
         }
       } else {
@@ -562,6 +569,7 @@ __global__ void __launch_bounds__(PT, 1) sweep_pencil_kernel(const kb200_sweep_d
     }
   }
 #undef TL
+#undef ITEM
 }
 
 }  // namespace kb200
@@ -584,6 +592,10 @@ int kb200_sweep_pencil_try(const kb200_sweep_desc *h, int n, const void *d_descs
   gm.layout = layout; gm.Ds = h[0].Ds; gm.Gs = h[0].Gs; gm.ni = h[0].ni; gm.nj = h[0].nj; gm.nk = h[0].nk;
   if ((double)gm.Ds * gm.Gs * gm.ni * gm.nj * gm.nk >= 2147483648.0) return -1;  // 32-bit element offsets
   { const char *x = getenv("KB200_PENCIL_EXP"); gm.exp = x ? atoi(x) : 0; }
+  // measured at BASELINE config 2: ZGD 16.0 -> 14.8 ms with interleaved items (a zone's 24 slices are one 6 KB run that
+  // 24 neighbouring CTAs then stream together), GZD 18.9 -> 19.1 ms (its slices are 12 KB apart anyway)
+  gm.interleave = (layout == 4 || layout == 5) ? 1 : 0;
+  { const char *x = getenv("KB200_PENCIL_INTERLEAVE"); if (x) gm.interleave = (x[0] == '1') ? 1 : 0; }
   gm.j_tiles = (gm.nj + PTJ - 1) / PTJ;
   gm.k_tiles = (gm.nk + PTK - 1) / PTK;
   const int E = gm.Ds * gm.Gs;

@@ -524,6 +524,15 @@ class Timing : public Core::BaseVar {
     size_t count = 0;
   };
   std::map<std::string, Timer> timers;
+  // nested regions, as the reference's Caliper annotations record them (Timing.h:93-109: every KRIPKE_TIMER is also a
+  // nested "kripke" region): inclusive seconds per call path.  Printed as a runtime-report style tree when CALI_CONFIG or
+  // CALI_CONFIG_PROFILE asks for "runtime-report" (README.md:182-186 of the reference).
+  std::vector<std::string> m_stack;                 // currently open regions, outermost first
+  std::vector<std::pair<std::string, double>> m_open;  // their paths and start times
+  std::map<std::string, double> m_region_seconds;   // "Solve/SweepSolver/SweepSubdomain" -> inclusive seconds
+  std::vector<std::string> m_region_order;          // paths in order of first entry
+ public:
+  void printRegions(void) const;
 };
 class BlockTimer {
  public:

@@ -74,13 +74,27 @@ void Timing::start(std::string const &name) {
   t.t0 = wallSeconds();
   t.started = true;
   ++t.count;
+  m_stack.push_back(name);
+  std::string path;
+  for (auto &n : m_stack) path += (path.empty() ? "" : "/") + n;
+  if (!m_region_seconds.count(path)) { m_region_seconds[path] = 0.0; m_region_order.push_back(path); }
+  m_open.emplace_back(path, t.t0);
 }
 void Timing::stop(std::string const &name) {
   Timer &t = timers[name];
   if (!t.started) return;
   if (s_sync) kb200_device_sync();
-  t.elapsed += wallSeconds() - t.t0;
+  const double now = wallSeconds();
+  t.elapsed += now - t.t0;
   t.started = false;
+  // close the innermost open region of that name (and anything left open inside it)
+  for (size_t k = m_stack.size(); k-- > 0;)
+    if (m_stack[k] == name) {
+      for (size_t q = m_stack.size(); q-- > k;) m_region_seconds[m_open[q].first] += now - m_open[q].second;
+      m_stack.resize(k);
+      m_open.resize(k);
+      break;
+    }
 }
 void Timing::stopAll(void) {
   for (auto &kv : timers) stop(kv.first);
@@ -108,6 +122,29 @@ void Timing::print(void) const {
   printf("\nTIMER_DATA:");
   for (size_t i = 0; i < names.size(); ++i) printf("%s%lf", i ? "," : "", getTotal(names[i]));
   printf("\n");
+  const char *c1 = getenv("CALI_CONFIG"), *c2 = getenv("CALI_CONFIG_PROFILE");
+  if ((c1 && strstr(c1, "runtime-report")) || (c2 && strstr(c2, "runtime-report"))) printRegions();
+}
+// the table Caliper's runtime-report prints for the reference's nested regions: one row per call path, indented by depth
+void Timing::printRegions(void) const {
+  double total = 0.0;
+  for (auto &p : m_region_order)
+    if (p.find('/') == std::string::npos) total += m_region_seconds.at(p);
+  printf("\n%-36s %13s %13s %13s %7s\n", "Path", "Min time/rank", "Max time/rank", "Avg time/rank", "Time %");
+  std::vector<std::string> order = m_region_order;
+  std::sort(order.begin(), order.end());  // parents before children, siblings by name
+  for (auto &p : order) {
+    const size_t depth = std::count(p.begin(), p.end(), '/');
+    const std::string leaf = p.substr(p.rfind('/') == std::string::npos ? 0 : p.rfind('/') + 1);
+    const double s = m_region_seconds.at(p);
+    // exclusive share of the run, as runtime-report shows it
+    double child = 0.0;
+    for (auto &q : m_region_order)
+      if (q.size() > p.size() && q.compare(0, p.size(), p) == 0 && q[p.size()] == '/' && q.find('/', p.size() + 1) == std::string::npos)
+        child += m_region_seconds.at(q);
+    const std::string label = std::string(2 * depth, ' ') + leaf;
+    printf("%-36s %13.6f %13.6f %13.6f %7.3f\n", label.c_str(), s, s, s, total > 0.0 ? 100.0 * (s - child) / total : 0.0);
+  }
 }
 
 // ---- InputVariables (src/Kripke/InputVariables.cpp) -------------------------------------------------------

@@ -459,6 +459,14 @@ def test_kripke_exe_command_line_and_output(gpu, goldens):
     assert all(float(x) >= 0.0 for x in data)
     assert "Figures of Merit" in out.stdout and "Grind time" in out.stdout and "Number of unknowns: 12582912" in out.stdout
     assert out.stdout.rstrip().endswith("END")
+    assert "Min time/rank" not in out.stdout
+    # Caliper's runtime-report of the reference's nested regions (Timing.h:93-109, README "CALI_CONFIG_PROFILE")
+    env = dict(os.environ, CALI_CONFIG_PROFILE="runtime-report")
+    out = subprocess.run([exe] + g["args"].split(), capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0
+    rows = [l for l in out.stdout.splitlines() if re.match(r"^\s*(Generate|Solve|LTimes|LPlusTimes|Scattering|Source|SweepSolver|SweepSubdomain|Population)\s", l)]
+    tree = {l.split()[0]: len(l) - len(l.lstrip()) for l in rows if "Timer" not in l}
+    assert "Path" in out.stdout and tree["Solve"] == 0 and tree["SweepSolver"] == 2 and tree["SweepSubdomain"] == 4 and tree["LTimes"] == 2
 
 
 GEN_ZONE_FIELDS = ["sigt_zonal", "volume", "zone_to_num_mixelem", "zone_to_mixelem", "mixelem_to_zone", "mixelem_to_material",
