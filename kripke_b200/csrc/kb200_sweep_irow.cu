@@ -685,9 +685,19 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
   const int by_smem = (int)((227 * 1024) / (smem + 1024));
   if (per_sm > by_smem) per_sm = by_smem;
   if (per_sm < 1) per_sm = 1;
-  int cps = (int)(((long long)sm_count() * per_sm) / n);
-  if (cps < 1) cps = 1;
-  if (cps > ngroups) cps = ngroups;
+  // CTAs per subdomain: minimise waves x (element groups per CTA + the fixed cost of a CTA, about one and a half groups'
+  // worth of prologue and pipeline fill).  With many small subdomains in a batch (BASELINE config 4: ~90 subdomains of
+  // 16^3 zones per stage) "one CTA per subdomain" would leave a third of the SMs idle.
+  int cps = 1;
+  {
+    const long long slots = (long long)sm_count() * per_sm;
+    double best = -1.0;
+    for (int c = 1; c <= ngroups; ++c) {
+      const long long waves = ((long long)c * n + slots - 1) / slots;
+      const double cost = (double)waves * ((double)((ngroups + c - 1) / c) + 1.5);
+      if (best < 0.0 || cost < best - 1e-9) { best = cost; cps = c; }
+    }
+  }
   double *pp = d_pop_partial;
   if (pp && (long long)cps * n > pop_capacity) pp = nullptr;
   if (pop_count) *pop_count = pp ? cps * n : 0;
