@@ -50,6 +50,9 @@ def abi():
         L.kb200_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.kb200_fill_f64.argtypes = [C.c_void_p, C.c_double, C.c_size_t, C.c_void_p]
         L.kb200_stream_sync.argtypes = [C.c_void_p]
+        L.kb200_stream_create.argtypes = [C.POINTER(C.c_void_p)]
+        L.kb200_stream_destroy.argtypes = [C.c_void_p]
+        L.kb200_stream_wait_event.argtypes = [C.c_void_p, C.c_void_p]
         L.kb200_event_create.argtypes = [C.POINTER(C.c_void_p)]
         L.kb200_event_destroy.argtypes = [C.c_void_p]
         L.kb200_event_record.argtypes = [C.c_void_p, C.c_void_p]

@@ -383,6 +383,10 @@ void SweepComm::markComplete(SdomId sdom_id) {
 // exchanged are all zeros, so every subdomain is swept with zero inflow on all three faces; the
 // exchange is still performed once per iteration (communication-pattern proxy).
 BlockJacobiComm::BlockJacobiComm(DataStore &data_store) : ParallelComm(data_store), posted_sends(false) {
+  {
+    Comm comm;
+    if (comm.size() > 1) PeerExchange::get(data_store)->beginSweep();  // collective on first use; a new epoch of flags
+  }
   ArchLayoutV al_v = data_store.getVariable<ArchLayout>("al").al_v;
   createField<Field_IPlane>(data_store, "old_i_plane", al_v, data_store.getVariable<Set>("Set/IPlane"));
   createField<Field_JPlane>(data_store, "old_j_plane", al_v, data_store.getVariable<Set>("Set/JPlane"));
@@ -393,6 +397,10 @@ BlockJacobiComm::BlockJacobiComm(DataStore &data_store) : ParallelComm(data_stor
   Kernel::kConst(data_store.getVariable<Field_KPlane>("old_k_plane"), 0.0);
 }
 BlockJacobiComm::~BlockJacobiComm() {
+  {
+    Comm comm;  // a peer may overwrite a plane chunk on this GPU only when every rank is done reading
+    if (comm.size() > 1 && PeerExchange::get(*m_data_store)->usable()) KB200_CALL(kb200_comm_barrier(nullptr));
+  }
   KB200_CALL(kb200_stream_sync(nullptr));
   m_data_store->deleteVariable("old_i_plane");
   m_data_store->deleteVariable("old_j_plane");
@@ -408,34 +416,48 @@ bool BlockJacobiComm::workRemaining(void) {
     // on-rank neighbours: dependency bookkeeping + (zero) copy, exactly one pass over the queue
     std::vector<int> ids = queue_sdom_ids;
     for (int id : ids) postSends(*m_data_store, SdomId(id), old_planes);
-    // off-rank neighbours: one grouped exchange of the old planes per iteration
+    // off-rank neighbours: one exchange of the old planes per iteration -- peer-memory copies straight into the
+    // neighbours' plane chunks with device-side flags, or (fallback) one grouped NCCL exchange
     auto &pspace = m_data_store->getVariable<PartitionSpace>("pspace");
     Comm comm;
     if (comm.size() > 1) {
       auto &f_up = m_data_store->getVariable<Field_Adjacency>("upwind");
       auto &f_down = m_data_store->getVariable<Field_Adjacency>("downwind");
       const long *l2g = m_data_store->getVariable<Field_SdomId2GlobalSdomId>("SdomId2GlobalSdomId").getDataConst(SdomId(0));
+      PeerExchange *px = PeerExchange::get(*m_data_store);
       std::vector<Message> msgs;
+      std::vector<SdomId> all;
       for (int id : ids) {
         SdomId sdom(id);
+        all.push_back(sdom);
         const long *down = f_down.getDataConst(sdom), *up = f_up.getDataConst(sdom);
         for (int dim = 0; dim < 3; ++dim) {
           if (down[dim] >= 0) {
             int peer = pspace.globalSdomIdToRank(GlobalSdomId(down[dim]));
-            if (peer != (int)comm.rank())
-              msgs.push_back(Message{down[dim], dim, peer, true, old_planes[dim]->devicePtr(sdom), old_planes[dim]->size(sdom)});
+            if (peer != (int)comm.rank()) {
+              if (px->usable())
+                KB200_CALL(kb200_copy(px->outPlane(sdom, dim), old_planes[dim]->devicePtr(sdom), old_planes[dim]->size(sdom) * sizeof(double), nullptr));
+              else
+                msgs.push_back(Message{down[dim], dim, peer, true, old_planes[dim]->devicePtr(sdom), old_planes[dim]->size(sdom)});
+            }
           }
           if (up[dim] >= 0) {
             int peer = pspace.globalSdomIdToRank(GlobalSdomId(up[dim]));
             if (peer != (int)comm.rank()) {
-              msgs.push_back(Message{l2g[id], dim, peer, false, m_plane_data[dim]->devicePtrOverwrite(sdom), m_plane_data[dim]->size(sdom)});
+              if (px->usable()) m_plane_data[dim]->devicePtrOverwrite(sdom);  // defined by the peer's copy
+              else msgs.push_back(Message{l2g[id], dim, peer, false, m_plane_data[dim]->devicePtrOverwrite(sdom), m_plane_data[dim]->size(sdom)});
               for (size_t i = 0; i < queue_sdom_ids.size(); ++i)
                 if (queue_sdom_ids[i] == id) { queue_depends[i]--; break; }
             }
           }
         }
       }
-      runExchange(msgs);
+      if (px->usable()) {
+        px->signal(all);
+        px->wait(all);
+      } else {
+        runExchange(msgs);
+      }
     }
     posted_sends = true;
   }
