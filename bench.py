@@ -90,7 +90,8 @@ def measured_peaks():
 
 
 def ncu_traffic(workload, layout, kernel):
-    """DRAM bytes (read + write) per launch of the entry point's kernel from the committed `ncu --set full` capture of the
+    """DRAM bytes (read + write) per call of the entry point (one launch, or the eleven tile-diagonal launches of the pencil
+    sweep) from the committed `ncu --set full` capture of the
     same workload (profiles/ncu_traffic.json, written by tools/ncu_traffic.py), and where that number comes from: the
     capture file and the commit it was taken at.  (None, None) if no capture of this workload/layout exists -- a number
     measured under a profiler cannot be produced inside a timing run."""
@@ -98,8 +99,10 @@ def ncu_traffic(workload, layout, kernel):
     try:
         with open(path) as f:
             e = json.load(f)[f"{workload}:{layout}"]
-        return e["per_entry_point"][kernel]["dram_bytes_per_launch"], {"file": "profiles/ncu_traffic.json", "capture": e.get("source"),
-                                                                      "commit": e.get("commit")}
+        k = e["per_entry_point"][kernel]
+        # the capture holds exactly one source iteration: the sum over the entry point's launches is its traffic per call
+        return k["dram_bytes"], {"file": "profiles/ncu_traffic.json", "capture": e.get("source"), "commit": e.get("commit"),
+                                 "launches_per_call": k["launches"]}
     except Exception:
         return None, None
 

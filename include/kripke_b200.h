@@ -50,6 +50,7 @@ int kb200_device_info(char *name, size_t name_len, int *sm_count, int *cc_major,
                       size_t *free_bytes, size_t *total_bytes);
 int kb200_alloc(size_t bytes, void **d_ptr);      /* Field.h:69  new ElementType[sdom_size] */
 int kb200_free(void *d_ptr);                      /* Field.h:98-104 */
+int kb200_pool_trim(void);                        /* return the pooled free blocks (at most 4 GB) to the driver */
 int kb200_alloc_host(size_t bytes, void **h_ptr); /* pinned host memory for mirrors / e2e staging */
 int kb200_free_host(void *h_ptr);
 int kb200_upload(void *d_dst, const void *h_src, size_t bytes, kb200_stream_t stream);

@@ -302,8 +302,7 @@ void clear_pool() {
   std::lock_guard<std::mutex> lock(g_pool_mutex);
   for (auto &kv : g_pool_free)
     for (void *q : kv.second) cudaFree(q);
-  g_pool_free.clear();
-  g_pool_sizes.clear();
+  g_pool_free.clear();  // live blocks stay tracked in g_pool_sizes: they may still be pooled when freed
   g_pool_bytes = 0;
 }
 }  // namespace
@@ -359,6 +358,12 @@ int kb200_free(void *p) {
     }
   }
   KB_CUDA(cudaFree(p));
+  return 0;
+}
+// give the pooled (free) blocks back to the driver; live blocks are untouched
+int kb200_pool_trim(void) {
+  KB_CUDA(cudaDeviceSynchronize());
+  clear_pool();
   return 0;
 }
 int kb200_alloc_host(size_t bytes, void **p) {

@@ -204,6 +204,19 @@ __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scatter
 
     if (st == nst - 1) {
       const int ncol = tn * NT + ncol0 + 2 * (lane & 3);
+      // Kernel::source folded in (Kernel/Source.cpp:59-75): phi_out(0,g,z) += strength * fraction of material 0, the same for
+      // every group; zero for the other moments (x + 0.0 leaves x's bits alone)
+      double sx[NB][2];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        sx[nb][0] = sx[nb][1] = 0.0;
+        const int n = ncol + 8 * nb;
+        if (gm.source != 0.0 && b == 0 && n < gm.Zs) {
+          const double *f0 = fractions + (size_t)blockIdx.y * 3 * gm.Zs + n;
+          sx[nb][0] = gm.source * __ldg(f0);
+          sx[nb][1] = gm.source * __ldg(f0 + 1);
+        }
+      }
 #pragma unroll
       for (int a = 0; a < QP; ++a) {
         const int o = 8 * a + (lane >> 2);
@@ -213,12 +226,7 @@ __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scatter
           for (int nb = 0; nb < NB; ++nb) {
             const int n = ncol + 8 * nb;
             if (n < gm.Zs) {
-              double2 v = make_double2(acc[a][nb][0], acc[a][nb][1]);
-              if (gm.source != 0.0 && b == 0) {  // Kernel/Source.cpp:59-75: phi_out(0,g,z) += strength * fraction of material 0
-                const double *f0 = fractions + (size_t)blockIdx.y * 3 * gm.Zs + n;
-                v.x = fma(gm.source, __ldg(f0), v.x);
-                v.y = fma(gm.source, __ldg(f0 + 1), v.y);
-              }
+              double2 v = make_double2(acc[a][nb][0] + sx[nb][0], acc[a][nb][1] + sx[nb][1]);
               double2 *p = reinterpret_cast<double2 *>(row + n);
               if (gm.accumulate) { const double2 old = *p; v.x += old.x; v.y += old.y; }
               *p = v;

@@ -51,6 +51,8 @@ constexpr int IROW_MAXW = 16, IROW_MAXT = IROW_MAXW * 32;  // warps per CTA: up 
 struct IGeom {  // kernel parameter: lives in the constant bank, costs no registers
   int layout, Ds, Gs, ni, nj, nk;
   int NW, nkt;  // warps (= k-planes) per CTA, k tiles
+  int lra;      // lanes of a row segment that really hold zones (ni / 4); the template's LR is the next power of two and the
+                // lanes beyond lra idle at the end of their segment (their maps only reach other idle lanes in the scan)
   int E, ngroups;
   unsigned sb, vol_off;  // bytes of one staging slot and offset of the zone-volume rows in it
   int sig1;              // the ER rows of a warp always share their group (Ds % ER == 0): one sigt row (pair) per step
@@ -173,7 +175,8 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int seg = lane / LR, ls = lane % LR;
   const int NW = gm.NW, ni = gm.ni, nj = gm.nj, nk = gm.nk, nkt = gm.nkt;
-  const unsigned i0 = FWD ? 4u * ls : (unsigned)(ni - 4 - 4 * ls);  // memory position of this lane's four zones
+  const bool act = ls < gm.lra;  // this lane holds zones (ni need not be 4 * 2^k)
+  const unsigned i0 = !act ? 0u : (FWD ? 4u * ls : (unsigned)(ni - 4 - 4 * ls));  // memory position of this lane's four zones
   const int jd = ds.jd, kd = ds.kd;
   const bool i_zero = ds.inflow_zero[0] != 0, j_zero = ds.inflow_zero[1] != 0, k_zero = ds.inflow_zero[2] != 0;
   const int jstep = (jd > 0) ? ni : -ni;
@@ -264,7 +267,8 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
   if (nx_ok && nx.kv && !i_zero) fi0n = ir_ld_cg(ds.i_plane + nx.ipx0);
 
   while (nx_ok) {
-    const IItem it = nx;
+    IItem it = nx;
+    it.ev = it.ev && act;  // idle lanes compute on shadow data and store nothing
     const bool ktile0 = (t == 0);
     // the item after this one
     int ngi = gi, nt = t + 1;
@@ -437,7 +441,7 @@ __device__ __forceinline__ double irow_run(const kb200_sweep_desc &ds, const IGe
           for (int u = 0; u < 4; ++u) pop = fma(wd * p4[u], v4[u], pop);
         }
         if (POPM == 2) psum += (p4[0] + p4[1]) + (p4[2] + p4[3]);
-        if (ls == LR - 1) {
+        if (ls == gm.lra - 1) {
           ds.i_plane[ipx] = fo;
           if (ds.out_plane[0]) ds.out_plane[0][ipx] = fo;
         }
@@ -629,8 +633,10 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
   if (env && env[0] == '0') return -1;
   const int ni = h[0].ni, nj = h[0].nj, nk = h[0].nk;
   if (ni % 4 != 0) return -1;
-  const int LR = ni / 4;
-  if (LR > 32 || (LR & (LR - 1)) != 0) return -1;
+  const int lra = ni / 4;  // lanes per row; the kernel is instantiated for the next power of two
+  if (lra > 32) return -1;
+  int LR = 1;
+  while (LR < lra) LR <<= 1;
   for (int i = 0; i < n; ++i) {
     const void *ptrs[] = {h[i].rhs, h[i].psi, h[i].sigt, h[i].j_plane, h[i].k_plane, h[i].out_plane[1], h[i].out_plane[2]};
     for (const void *p : ptrs)
@@ -650,6 +656,7 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
     gm.kpd = (unsigned)kps.d; gm.kpg = (unsigned)kps.g;
     gm.E = gm.Ds * gm.Gs;
   }
+  gm.lra = lra;
   gm.nkt = (nk + IROW_MAXW - 1) / IROW_MAXW;
   gm.NW = (nk + gm.nkt - 1) / gm.nkt;
   // rows are fetched IROW_PD steps ahead, at most into the next item; warp 0 must not wait for tile-boundary
@@ -670,7 +677,7 @@ int kb200_sweep_irow_try(const kb200_sweep_desc *h, int n, const void *d_descs, 
     gm.vol_off = rb + ((pair && gm.sig1) ? 2u * rowb : rb);  // a shared sigt row pair takes 2*rowb instead of a full block
     gm.sb = gm.vol_off + ((d_pop_partial && !volu) ? (pair ? 2u : 1u) * rowb : 0u);
     // swizzled staging (tensor maps): 1 KB row pairs per segment, every slot a multiple of 1 KB from a 1 KB aligned base
-    swz = pair && LR >= 16 && !(se && se[0] == '0') && encode_tiled() != nullptr;
+    swz = pair && LR >= 16 && lra == LR && !(se && se[0] == '0') && encode_tiled() != nullptr;
     if (swz) gm.sb = (gm.sb + 1023u) & ~1023u;
     const size_t align_slack = swz ? 1024 : 0;
     smem = (size_t)IROW_RING * (gm.NW + 1) * rb + (size_t)4 * 1024 + (size_t)gm.NW * (pair ? 2 : IROW_NS) * gm.sb +

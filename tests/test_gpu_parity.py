@@ -148,6 +148,11 @@ ZLINE_CASES = [
     "--zones 64,6,5 --groups 3 --quad 8 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",      # 16 lanes per row, odd element count
     "--zones 128,4,3 --groups 2 --quad 8 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",     # one row per warp (32-lane scan)
     "--zones 32,34,33 --groups 2 --quad 8 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",    # 8 lanes per row, k tiles 17+16
+    # rows whose lane count is not a power of two ride in the next larger segment with idle lanes at its end:
+    "--zones 48,6,5 --groups 3 --quad 8 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",      # 12 of 16 lanes, odd nk
+    "--zones 24,8,18 --groups 2 --quad 16 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",    # 6 of 8 lanes, row pairs, two k tiles
+    "--zones 96,4,3 --groups 2 --quad 8 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",      # 24 of 32 lanes
+    "--zones 20,7,4 --groups 2 --quad 8 --legendre 0 --gset 1 --dset 8 --zset 1,1,1",      # 5 of 8 lanes, odd nj (single rows)
 ]
 
 
@@ -349,10 +354,12 @@ def test_fused_population_abi_matches_separate_kernel(gpu):
 def test_device_allocation_pool_reuses_blocks(gpu):
     A = gpu.abi()
     a, b = C.c_void_p(), C.c_void_p()
-    assert A.kb200_alloc(1 << 20, C.byref(a)) == 0
+    size = (1 << 20) + 7 * 4096  # a size nothing else in the suite pools
+    assert A.kb200_pool_trim() == 0  # the pool keeps at most 4 GB: start from an empty one
+    assert A.kb200_alloc(size, C.byref(a)) == 0
     first = a.value
     assert A.kb200_free(a) == 0
-    assert A.kb200_alloc(1 << 20, C.byref(b)) == 0
+    assert A.kb200_alloc(size, C.byref(b)) == 0
     assert b.value == first               # same size: the pooled block comes back, no cudaMalloc
     big = C.c_void_p()
     assert A.kb200_alloc(96 << 20, C.byref(big)) == 0 and A.kb200_free(big) == 0   # above the pool limit: plain cudaFree
