@@ -123,6 +123,8 @@ int kb200_scattering(const kb200_scattering_desc *h_descs, int n, kb200_stream_t
  * receives strength * (volume fraction of material 0 in the zone).  *folded = 1: done, kb200_source must not follow;
  * *folded = 0: the kernel in use cannot fold (bit-exact mode, odd shapes) and only the scattering was done. */
 int kb200_scattering_source(const kb200_scattering_desc *h_descs, int n, double strength, int *folded, kb200_stream_t stream);
+/* kernel family that served the last scattering call: "slab", "mma", "transposed+slab", "transposed+mma" or "dfma" */
+const char *kb200_last_scattering_kernel(void);
 
 /* ---- Source: Kripke::Kernel::source (src/Kripke/Kernel/Source.cpp:83-115, body :59-75) ----
  * phi_out(0,g,zone(mix)) += strength * fraction(mix) for every mixelem of material 0.

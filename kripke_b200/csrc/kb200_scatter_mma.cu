@@ -249,10 +249,17 @@ __global__ void __launch_bounds__(256, 2) scatter_mma_kernel(const kb200_scatter
 
 using namespace kb200;
 
+extern "C" const char *g_last_scattering_kernel;  // kb200_scatter_pop.cu
+int kb200_scatter_slab_try(const kb200_scattering_desc *h, int n, const void *d_descs, int sigs_layout, double source, cudaStream_t st);  // kb200_scatter_slab.cu
+
 // Returns 0 if handled, -1 if this path does not apply (caller falls back to the DFMA kernel), >0 on error.
 int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_descs, int sigs_layout, double source, cudaStream_t st) {
   const int layout = h[0].layout;
   if (layout != 0 && layout != 2) return -1;
+  {  // the one-read kernel first (descriptor groups, whole-K stages); it declines what it does not cover
+    const int rc = kb200_scatter_slab_try(h, n, d_descs, sigs_layout, source, st);
+    if (rc != -1) { g_last_scattering_kernel = "slab"; return rc; }
+  }
   const char *env = getenv("KB200_SCATTER_DFMA");
   if (env && env[0] == '1') return -1;
   if (h[0].Zs % 2 != 0) return -1;
@@ -302,5 +309,6 @@ int kb200_scatter_mma_try(const kb200_scattering_desc *h, int n, const void *d_d
   dim3 grid((unsigned)ctas, n, nochunks);
   if (QP == 2) scatter_mma_kernel<2><<<grid, 256, smem, st>>>((const kb200_scattering_desc *)d_descs, gm, g_frac_scratch);
   else scatter_mma_kernel<4><<<grid, 256, smem, st>>>((const kb200_scattering_desc *)d_descs, gm, g_frac_scratch);
+  g_last_scattering_kernel = "mma";
   return post_launch("scatter_mma");
 }

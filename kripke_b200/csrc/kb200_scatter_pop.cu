@@ -284,6 +284,10 @@ int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, double source, 
 extern "C" {
 
 static int scattering_impl(const kb200_scattering_desc *h, int n, double source, int *folded, kb200_stream_t stream);
+// which kernel family served the last scattering call: "slab" (one-read tensor-core kernel), "mma" (per-descriptor
+// tensor-core kernel), "transposed+slab" / "transposed+mma" (moment-fastest nestings), "dfma" (bit-exact / odd shapes)
+const char *g_last_scattering_kernel = "none";
+const char *kb200_last_scattering_kernel(void) { return g_last_scattering_kernel; }
 int kb200_scattering(const kb200_scattering_desc *h, int n, kb200_stream_t stream) {
   return scattering_impl(h, n, 0.0, nullptr, stream);
 }
@@ -312,11 +316,16 @@ static int scattering_impl(const kb200_scattering_desc *h, int n, double source,
   int rc = device_descs(h, sizeof(*h) * n, &d, st);
   if (rc) return rc;
   if (!exact_mode()) {  // default arithmetic: fp64 tensor-core path for the zone-fastest layouts
-    rc = kb200_scatter_mma_try(h, n, d, -1, source, st);
+    rc = kb200_scatter_mma_try(h, n, d, -1, source, st);  // sets g_last_scattering_kernel to "slab" or "mma"
     if (rc >= 0) { if (folded && rc == 0 && source != 0.0) *folded = 1; return rc; }
     rc = kb200_scatter_row_try(h, n, source, st);  // moment-fastest layouts: transposed through the zone-fastest kernel
-    if (rc >= 0) { if (folded && rc == 0 && source != 0.0) *folded = 1; return rc; }
+    if (rc >= 0) {
+      g_last_scattering_kernel = !strcmp(g_last_scattering_kernel, "slab") ? "transposed+slab" : "transposed+mma";
+      if (folded && rc == 0 && source != 0.0) *folded = 1;
+      return rc;
+    }
   }
+  g_last_scattering_kernel = "dfma";
   constexpr int GT = 8;
   long long total = (long long)h[0].M * h[0].Zs;
   dim3 grid((unsigned)((total + 127) / 128), (h[0].Gs + GT - 1) / GT, n);

@@ -444,6 +444,40 @@ def test_scattering_at_config2_group_structure(gpu, layout):
     assert_close(p.field("phi_out"), o.field("phi_out"), f"scattering accumulate {layout}", False)
 
 
+SLAB_CASES = [
+    # (arguments, kernel family expected in DGZ)                                                      what the shape exercises
+    ("--zones 12,8,10 --groups 64 --quad 8 --legendre 4 --gset 2 --zset 1,2,1", "slab"),   # config 2: 64 outputs in one CTA, two zone sets, ragged last tile
+    ("--zones 16,8,6 --groups 64 --quad 8 --legendre 2 --gset 4 --zset 2,1,1", "slab"),    # config 4: four destination sets of 16 groups per CTA
+    ("--zones 20,6,6 --groups 128 --quad 8 --legendre 2 --gset 1 --zset 1,1,1", "slab"),   # config 3: four sibling CTAs of 32 outputs, 4 stages per tile
+    ("--zones 12,6,6 --groups 96 --quad 8 --legendre 1 --gset 3 --zset 1,1,2", "slab"),    # three siblings, K = 96 (3 stages of 32)
+    ("--zones 12,10,6 --groups 32 --quad 8 --legendre 3 --gset 1 --zset 1,1,1", "slab"),   # config 1 / 5: one 32-output CTA, K = 32
+    ("--zones 12,10,6 --groups 36 --quad 8 --legendre 1 --gset 1 --zset 1,1,1", "mma"),    # outputs not a multiple of 32: per-descriptor kernel
+    ("--zones 10,9,7 --groups 32 --quad 8 --legendre 1 --gset 1 --zset 1,1,1", "mma"),     # zone count not a multiple of 4
+]
+
+
+@pytest.mark.parametrize("layout", ["DGZ", "GDZ", "ZGD"])
+@pytest.mark.parametrize("case", range(len(SLAB_CASES)))
+def test_scattering_one_read_kernel_shapes(gpu, case, layout):
+    """kb200_scatter_slab.cu (one staged read of the source moments for all destination group sets; sibling CTAs where the
+    matrices of all outputs do not fit) against the oracle: dense asymmetric sigs, mixed-material zones, source folded in
+    through the solver's entry point, then '+=' on top; shapes it declines must land on the per-descriptor kernel."""
+    args, family = SLAB_CASES[case]
+    p, o, _, _ = pair(gpu, f"{args} --dset 8 --layout {layout}")
+    A = gpu.abi()
+    A.kb200_last_scattering_kernel.restype = C.c_char_p
+    fill_both(p, o, "data/sigs", 9100 + case, 0.0, 0.1)
+    fill_both(p, o, "phi", 9200 + case, -1.0, 1.0)
+    o.zero("phi_out"); o.scattering(); o.source()
+    p.call("zero:phi_out"); p.call("scattering"); p.call("source")
+    got = A.kb200_last_scattering_kernel().decode()
+    assert got == (family if layout != "ZGD" else "transposed+" + family), got
+    assert_close(p.field("phi_out"), o.field("phi_out"), f"scattering {layout} {args}", False)
+    o.scattering(); p.call("scattering")  # accumulate on top of the previous result
+    assert_close(p.field("phi_out"), o.field("phi_out"), f"scattering accumulate {layout} {args}", False)
+    p.close()
+
+
 def test_kripke_exe_command_line_and_output(gpu, goldens):
     """the drop-in executable: the reference's command line in, the reference's iteration lines, TIMER_NAMES/TIMER_DATA
     and figures of merit out (src/kripke.cpp:480-516, SteadyStateSolver.cpp:86-90, Timing.cpp:78-95)."""
@@ -503,12 +537,13 @@ def test_device_generator_matches_host_generator_at_scale(gpu, monkeypatch):
         assert np.array_equal(dev.field(n), host.field(n)), n
 
 
+@pytest.mark.parametrize("groups", [8, 64])  # 64 groups in two sets: the one-read kernel (kb200_scatter_slab.cu)
 @pytest.mark.parametrize("layout", ["DGZ", "GDZ", "GZD", "ZGD"])
-def test_source_folded_into_scattering_matches_separate_kernels(gpu, monkeypatch, layout):
+def test_source_folded_into_scattering_matches_separate_kernels(gpu, monkeypatch, layout, groups):
     """SteadyStateSolver's scattering call adds Kernel::source's term in the epilogue of the tensor-core kernel
     (Kernel/Source.cpp:59-75 touches only the moment-0 slab that kernel has just written).  One iteration through the
     solver with and without the fold must leave bit-identical phi_out and rhs, and the same particle count."""
-    args = f"--zones 12,20,10 --groups 8 --quad 16 --legendre 2 --gset 2 --dset 8 --zset 1,2,1 --niter 2 --layout {layout}"
+    args = f"--zones 12,20,10 --groups {groups} --quad 16 --legendre 2 --gset 2 --dset 8 --zset 1,2,1 --niter 2 --layout {layout}"
     res = {}
     for fold in ("1", "0"):
         monkeypatch.setenv("KB200_FOLD_SOURCE", fold)
