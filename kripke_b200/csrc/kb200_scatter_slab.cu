@@ -19,6 +19,7 @@
 //   memory, never a correctness dependency), so the siblings' re-reads of a tile hit L2.
 // Anything this kernel does not cover (odd shapes, unaligned chunks, irregular descriptor lists) returns -1 and the
 // per-descriptor kernel of kb200_scatter_mma.cu runs instead.
+#include <type_traits>
 #include <vector>
 #include "kb200_common.cuh"
 
@@ -111,35 +112,36 @@ __global__ void slab_matrices_kernel(const double *__restrict__ sigs, Strides4 s
 // consecutive rows at two adjacent 16-byte columns, and with a pitch that is a multiple of 128 bytes those four rows would
 // share their banks (4-way conflict; ncu of the first version: 302 M of 486 M shared wavefronts were conflicts).
 // pitch = 32 (mod 128) spreads them over the 32 banks.
-constexpr int SL_STAGES = 3, SL_PITCH_PAD = 32, SL_STAGE_DOUBLES = 2048;
-__host__ __device__ constexpr int sl_stage_bytes(int NT) { return (SL_STAGE_DOUBLES / NT + 3) * (8 * NT + SL_PITCH_PAD); }
+constexpr int SL_STAGES = 3, SL_PITCH_PAD = 32;
+__host__ __device__ constexpr int sl_stage_rows(int NT, int NG) { return 4096 / NG / NT; }
+__host__ __device__ constexpr int sl_stage_bytes(int NT, int NG) { return (sl_stage_rows(NT, NG) + 3) * (8 * NT + SL_PITCH_PAD); }
 
-// NG groups of eight consumer warps (WO output blocks of 8*QP outputs x WN = 8/WO column blocks of 16 zones), each with
+// NG groups of WO x WN consumer warps (WO output blocks of 8*QP outputs x WN column blocks of 16 zones), each with
 // its own producer warp and its own ring of SL_STAGES stages.  A group works on a whole tile; the groups take the tiles of
 // the CTA in turn and share nothing but the material matrices, so while one is busy with its epilogue and the bookkeeping
 // of its next tile the other keeps the fp64 pipe fed (with a single set of warps all of them reach their epilogues
 // together -- the stage ring keeps them in step -- and the pipe idles for a third of the time).  The rings are separate
 // because an mbarrier wait names a phase only by its parity: a group waiting for a stage that another group has yet to
 // consume twice over would see the wait succeed on the older phase.
-template <int QP, int WO, int NG>
-__global__ void __launch_bounds__(32 * 9 * NG, 1) scatter_slab_kernel(SlabGeom gm, SlabTables tb) {
-  constexpr int NW = 8 * NG, WN = 8 / WO, NT = 16 * WN, KC = SL_STAGE_DOUBLES / NT;  // zones per tile, source groups per stage
-  constexpr int SL_THREADS = 32 * 9 * NG;
-  constexpr unsigned PITCH = 8 * NT + SL_PITCH_PAD, SL_STAGE_BYTES = sl_stage_bytes(NT), FRAC_OFF = KC * PITCH;
+template <int QP, int WO, int WN, int NG>
+__global__ void __launch_bounds__(32 * (WO * WN + 1) * NG, 1) scatter_slab_kernel(SlabGeom gm, SlabTables tb) {
+  constexpr int GW = WO * WN, NW = GW * NG, NT = 16 * WN, KC = sl_stage_rows(NT, NG);  // zones per tile, source groups per stage
+  constexpr int SL_THREADS = 32 * (GW + 1) * NG;
+  constexpr unsigned PITCH = 8 * NT + SL_PITCH_PAD, SL_STAGE_BYTES = sl_stage_bytes(NT, NG), FRAC_OFF = KC * PITCH;
   extern __shared__ __align__(128) unsigned char slm[];
   const unsigned ws_b = gm.ws_doubles * 8u;
   double *Ws = reinterpret_cast<double *>(slm);
   const unsigned stage0 = sl_smem(slm) + ws_b;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int grpw = warp < NW ? warp >> 3 : warp - NW;  // consumer group of this warp / the group this producer warp feeds
+  const int grpw = warp < NW ? warp / GW : warp - NW;  // consumer group of this warp / the group this producer warp feeds
   const unsigned ring0 = stage0 + (unsigned)grpw * (SL_STAGES * SL_STAGE_BYTES);
   const unsigned full0 = stage0 + NG * SL_STAGES * SL_STAGE_BYTES + (unsigned)grpw * (16u * SL_STAGES), empty0 = full0 + 8u * SL_STAGES;
   const int slot = blockIdx.x / gm.CS, sib = blockIdx.x - slot * gm.CS;
   const int per_b = gm.ngroups * gm.ntn;
 
-  if (lane < SL_STAGES && (warp & 7) == 0 && warp < NW) {  // the first warp of each group sets up the group's barriers
+  if (lane < SL_STAGES && warp >= NW) {  // each producer sets up the barriers of its group
     sl_mb_init(full0 + 8u * lane, 1u);
-    sl_mb_init(empty0 + 8u * lane, 8u);
+    sl_mb_init(empty0 + 8u * lane, (unsigned)GW);
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   // rows of a stage beyond K and columns beyond the zone count are never written by a copy: they must hold finite values
@@ -192,13 +194,15 @@ __global__ void __launch_bounds__(32 * 9 * NG, 1) scatter_slab_kernel(SlabGeom g
   }
 
   // ---- consumers ----
-  const int wg = warp & 7;
+  const int wg = warp - grpw * GW;
   const int wo = wg / WN, wn = wg - wo * WN;
   const int col0 = wn * 16, jq = lane >> 2, kq = lane & 3;
   const unsigned a_lane = sl_smem(Ws) + (unsigned)(wo * 3 * gm.nkc4 * 32) * (8u * QP) + 16u * lane;
   const unsigned b_lane = (unsigned)kq * PITCH + (unsigned)(col0 + 2 * jq) * 8u;
   const int ncta = (gm.ntiles - slot + gm.nslots - 1) / gm.nslots;  // tiles of this CTA: t = slot + i * nslots
   bool first = true;
+  double *op[QP];  // output rows of this lane in the zone set op_grp
+  int op_grp = -1;
   for (int b_lo = 0; b_lo < gm.M;) {
     // the moments [b_lo, b_hi) share their Legendre order, i.e. the material matrices
     const int n_leg = __ldg(tb.m2l + b_lo);
@@ -223,35 +227,56 @@ __global__ void __launch_bounds__(32 * 9 * NG, 1) scatter_slab_kernel(SlabGeom g
 #pragma unroll
       for (int a = 0; a < QP; ++a) acc[a][0][0] = acc[a][0][1] = acc[a][1][0] = acc[a][1][1] = 0.0;
       double sx[4] = {0.0, 0.0, 0.0, 0.0};
+      unsigned present = 0;
+      if (grp != op_grp) {
+        op_grp = grp;
+        double *const *orow = tb.orow + (size_t)grp * gm.Otot + (sib * WO + wo) * 8 * QP + jq;
+#pragma unroll
+        for (int a = 0; a < QP; ++a) op[a] = orow[8 * a];
+      }
 
       for (int st = 0; st < gm.nst; ++st) {
         const unsigned it = (unsigned)((i / NG) * gm.nst + st), s = it % SL_STAGES, ph = (it / SL_STAGES) & 1u;
         const unsigned sb = ring0 + s * SL_STAGE_BYTES;
         sl_mb_wait(full0 + 8u * s, ph);
         const int kc_lo = st * (KC / 4), nkc = min(KC / 4, gm.nkc4 - kc_lo);
-        // one pass per material present in this warp's 16 zones (nearly always one); absent zones carry a zero fraction
+        const unsigned fa0 = sb + FRAC_OFF + (unsigned)(col0 + 2 * jq) * 8u;
+        if (st == 0) {  // which materials occur in this warp's 16 zones (every stage of the tile carries the same fraction rows)
+          const double2 f0 = sl_lds128(fa0), f1 = sl_lds128(fa0 + PITCH), f2 = sl_lds128(fa0 + 2 * PITCH);
+          const unsigned mine = ((f0.x != 0.0 || f0.y != 0.0) ? 1u : 0u) | ((f1.x != 0.0 || f1.y != 0.0) ? 2u : 0u) |
+                                ((f2.x != 0.0 || f2.y != 0.0) ? 4u : 0u);
+          present = __reduce_or_sync(0xffffffffu, mine);
+          if (gm.exp & 1) present = 0;
+        }
+        // one pass per material present (nearly always one); absent zones carry a zero fraction
 #pragma unroll 1
         for (int m = 0; m < 3; ++m) {
-          const double2 fm = sl_lds128(sb + FRAC_OFF + (unsigned)m * PITCH + (unsigned)(col0 + 2 * jq) * 8u);
-          if (!__any_sync(0xffffffffu, fm.x != 0.0 || fm.y != 0.0) || (gm.exp & 1)) continue;
+          if (!((present >> m) & 1u)) continue;
+          const double2 fm = sl_lds128(fa0 + (unsigned)m * PITCH);
           unsigned ap = a_lane + (unsigned)((m * gm.nkc4 + kc_lo) * 32) * (8u * QP);
           unsigned bp = sb + b_lane;
+          // all 16 zones pure in this material (the usual case): the B fragments need no scaling
+          const bool pure = __all_sync(0xffffffffu, fm.x == 1.0 && fm.y == 1.0);
+          auto pass = [&](auto scaled) {
 #pragma unroll 4
-          for (int kc = 0; kc < nkc; ++kc, ap += 32u * 8u * QP, bp += 4u * PITCH) {
-            const double2 bv = sl_lds128(bp);
-            double af[QP];
+            for (int kc = 0; kc < nkc; ++kc, ap += 32u * 8u * QP, bp += 4u * PITCH) {
+              const double2 bv = sl_lds128(bp);
+              double af[QP];
 #pragma unroll
-            for (int a = 0; a < QP; a += 2) {
-              const double2 av = sl_lds128(ap + 256u * a);  // [a / 2][lane][a % 2]: 16 bytes per lane, lanes contiguous
-              af[a] = av.x; af[a + 1] = av.y;
-            }
-            const double b0 = bv.x * fm.x, b1 = bv.y * fm.y;
+              for (int a = 0; a < QP; a += 2) {
+                const double2 av = sl_lds128(ap + 256u * a);  // [a / 2][lane][a % 2]: 16 bytes per lane, lanes contiguous
+                af[a] = av.x; af[a + 1] = av.y;
+              }
+              const double b0 = decltype(scaled)::value ? bv.x * fm.x : bv.x, b1 = decltype(scaled)::value ? bv.y * fm.y : bv.y;
 #pragma unroll
-            for (int a = 0; a < QP; ++a) {
-              sl_dmma(acc[a][0][0], acc[a][0][1], af[a], b0);
-              sl_dmma(acc[a][1][0], acc[a][1][1], af[a], b1);
+              for (int a = 0; a < QP; ++a) {
+                sl_dmma(acc[a][0][0], acc[a][0][1], af[a], b0);
+                sl_dmma(acc[a][1][0], acc[a][1][1], af[a], b1);
+              }
             }
-          }
+          };
+          if (pure) pass(std::false_type{});
+          else pass(std::true_type{});
         }
         if (st == gm.nst - 1 && gm.source != 0.0 && b == 0) {
           // Kernel/Source.cpp:59-75: phi_out(0,g,z) += strength * fraction of material 0, for this lane's four output zones
@@ -266,11 +291,10 @@ __global__ void __launch_bounds__(32 * 9 * NG, 1) scatter_slab_kernel(SlabGeom g
       // epilogue: lane holds outputs 8a + jq at the four consecutive zones col0 + 4*kq + {0,1,2,3}
       const int z = tn * NT + col0 + 4 * kq;
       if (z < gm.Zs && !(gm.exp & 4)) {
-        double *const *orow = tb.orow + (size_t)grp * gm.Otot + (sib * WO + wo) * 8 * QP + jq;
         const long long off = (long long)b * gm.in_b + z;
 #pragma unroll
         for (int a = 0; a < QP; ++a) {
-          double *p = orow[8 * a] + off;
+          double *p = op[a] + off;
           double v0 = acc[a][0][0] + sx[0], v1 = acc[a][1][0] + sx[1], v2 = acc[a][0][1] + sx[2], v3 = acc[a][1][1] + sx[3];
           if (gm.accumulate) {
             double o0, o1, o2, o3;
@@ -333,7 +357,7 @@ int kb200_scatter_slab_try(const kb200_scattering_desc *h, int n, const void *d_
   const int Otot = nd * Gs, K = nsrc * Gs, nkc4 = (K + 3) / 4, Kp = 4 * nkc4;
   if (Otot % 32 != 0) return -1;
   // outputs per CTA: everything in one CTA if the three matrices fit next to the stages, else 32-output sibling chunks
-  const size_t smem_cap = 227 * 1024 - 2 * SL_STAGES * (size_t)sl_stage_bytes(128) - 256;  // NT = 128 has the larger stages
+  const size_t smem_cap = 227 * 1024 - 4 * SL_STAGES * (size_t)sl_stage_bytes(64, 4) - 256;  // the largest rings of the variants below
   int Octa = 0;
   if (Otot % 64 == 0 && (size_t)3 * Kp * 64 * 8 <= smem_cap) Octa = 64;
   else if ((size_t)3 * Kp * 32 * 8 <= smem_cap) Octa = 32;
@@ -341,9 +365,9 @@ int kb200_scatter_slab_try(const kb200_scattering_desc *h, int n, const void *d_
   const int CS = Otot / Octa;
   if (CS > 32 || CS > sm_count()) return -1;
   const int WO = Octa / 32, QP = 4;
-  int NG = 2;  // groups of eight consumer warps taking the tiles of a CTA in turn
-  { const char *we = getenv("KB200_SLAB_GROUPS"); if (we && atoi(we) == 1) NG = 1; }
-  const int WN = 8 / WO, NT = 16 * WN, KC = SL_STAGE_DOUBLES / NT;
+  int NG = 4;  // consumer groups taking the tiles of a CTA in turn (16 consumer warps in all; 8 with a single group)
+  { const char *we = getenv("KB200_SLAB_GROUPS"); if (we && (atoi(we) == 1 || atoi(we) == 2)) NG = atoi(we); }
+  const int WN = (NG == 1 ? 8 : 16 / NG) / WO, NT = 16 * WN, KC = sl_stage_rows(NT, NG);
 
   SlabGeom gm;
   memset(&gm, 0, sizeof(gm));
@@ -385,7 +409,7 @@ int kb200_scatter_slab_try(const kb200_scattering_desc *h, int n, const void *d_
   // scratch: fractions, matrices, progress counters
   const size_t frac_b = (size_t)ngroups * 3 * Zs * sizeof(double);
   const size_t wg_b = (size_t)h[0].L1 * CS * gm.ws_doubles * sizeof(double);
-  const size_t prog_b = ((size_t)gm.nslots * CS * 2 * sizeof(unsigned) + 255) & ~(size_t)255;
+  const size_t prog_b = ((size_t)gm.nslots * CS * 4 * sizeof(unsigned) + 255) & ~(size_t)255;
   const size_t need = frac_b + wg_b + prog_b;
   if (g_slab_scratch_bytes < need) {
     if (g_slab_scratch) { KB_CUDA(cudaDeviceSynchronize()); cudaFree(g_slab_scratch); g_slab_scratch = nullptr; g_slab_scratch_bytes = 0; }
@@ -413,17 +437,22 @@ int kb200_scatter_slab_try(const kb200_scattering_desc *h, int n, const void *d_
   if (rc) return rc;
   if (CS > 1) KB_CUDA(cudaMemsetAsync(tb.progress, 0, prog_b, st));
 
-  const size_t smem = (size_t)gm.ws_doubles * 8 + NG * (SL_STAGES * (size_t)sl_stage_bytes(NT) + 16 * SL_STAGES);
+  const size_t smem = (size_t)gm.ws_doubles * 8 + NG * (SL_STAGES * (size_t)sl_stage_bytes(NT, NG) + 16 * SL_STAGES);
   const unsigned grid = (unsigned)(gm.nslots * CS);
-#define SL_LAUNCH(WO_, NG_)                                                                                                        \
-  do {                                                                                                                           \
-    KB_CUDA(cudaFuncSetAttribute(scatter_slab_kernel<4, WO_, NG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    scatter_slab_kernel<4, WO_, NG_><<<grid, 32 * 9 * NG_, smem, st>>>(gm, tb);                                                  \
+#define SL_LAUNCH(WO_, WN_, NG_)                                                                                                      \
+  do {                                                                                                                              \
+    KB_CUDA(cudaFuncSetAttribute(scatter_slab_kernel<4, WO_, WN_, NG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    scatter_slab_kernel<4, WO_, WN_, NG_><<<grid, 32 * (WO_ * WN_ + 1) * NG_, smem, st>>>(gm, tb);                                  \
   } while (0)
-  if (WO == 2 && NG == 2) SL_LAUNCH(2, 2);
-  else if (WO == 2) SL_LAUNCH(2, 1);
-  else if (NG == 2) SL_LAUNCH(1, 2);
-  else SL_LAUNCH(1, 1);
+  if (WO == 2) {
+    if (NG == 4) SL_LAUNCH(2, 2, 4);
+    else if (NG == 2) SL_LAUNCH(2, 4, 2);
+    else SL_LAUNCH(2, 4, 1);
+  } else {
+    if (NG == 4) SL_LAUNCH(1, 4, 4);
+    else if (NG == 2) SL_LAUNCH(1, 8, 2);
+    else SL_LAUNCH(1, 8, 1);
+  }
 #undef SL_LAUNCH
   return post_launch("scatter_slab");
 }
