@@ -327,7 +327,8 @@ def main():
 
     kernels = ["LTimes", "scattering", "source", "LPlusTimes", "SweepSolver", "population"]
     A.kb200_last_sweep_kernel.restype = C.c_char_p
-    sweep_kernels = set()
+    A.kb200_last_scattering_kernel.restype = C.c_char_p
+    sweep_kernels, scattering_kernels = set(), set()
     ev = {}
     for k in kernels:
         a, b = C.c_void_p(), C.c_void_p()
@@ -354,6 +355,8 @@ def main():
                 A.kb200_event_record(ev[k][1], None)
             if k == "SweepSolver":
                 sweep_kernels.add(A.kb200_last_sweep_kernel().decode())
+            if k == "scattering":
+                scattering_kernels.add(A.kb200_last_scattering_kernel().decode())
             if k == "population":
                 particles.append(r)  # 8-byte device->host read of the step's result
         if timed:
@@ -447,6 +450,7 @@ def main():
                 "gpu_launches": int(launches.value),
                 "command": "kripke " + " ".join(kargs),
                 "sweep_kernel": "|".join(sorted(sweep_kernels)),
+                "scattering_kernel": "|".join(sorted(scattering_kernels)),
                 "clocks": clocks,
                 "roofline": {"kernel": dom, "bound": "hbm", "achieved": per_kernel[dom]["alg_GBs_per_gpu"], "peak": peak,
                              "unit": "GB/s", "frac": per_kernel[dom]["frac_of_hbm_peak"],

@@ -260,6 +260,12 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
     const int nkc = min(gm.nkc4 - kc_lo, KC / 4);
     const double *bbase = buf + (size_t)(lane & 3) * NTP + ncol0 + (lane >> 2);
 
+    double2 xin2[NB];  // XMODE 2: the reduction row K-1 at this lane's C-fragment columns, the same for every pass
+    if (XMODE == 2) {
+      const double *xr = buf + (size_t)(K - 1) * NTP + ncol0 + 2 * (lane & 3);
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) xin2[nb] = *reinterpret_cast<const double2 *>(xr + 8 * nb);
+    }
     for (int pass = 0; pass < gm.npass; ++pass) {
       if (st == 0 || gm.npass > 1) {
 #pragma unroll
@@ -270,6 +276,11 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
         for (int nb = 0; nb < NB; ++nb) px[nb] = 0.0;
       }
       const int ot0 = pass * QP;
+      double wk2[QP];  // XMODE 2: weights of the reduction row K-1 for this pass's output tiles
+      if (XMODE == 2) {
+#pragma unroll
+        for (int a = 0; a < QP; ++a) wk2[a] = (ot0 + a < q) ? wx[8 * (ot0 + a) + (lane >> 2)] : 0.0;
+      }
       const double *wf = Ws + ((size_t)kc_lo * q + ot0) * 32 + lane;
       const double *brow = bbase;
       if (ot0 + QP <= q) {  // full pass: no per-tile predicates
@@ -310,17 +321,14 @@ __global__ void __launch_bounds__(256, (QP <= 4 ? 2 : 1)) moments_mma_kernel(con
           }
         }
       }
-      if (XMODE == 2) {  // the reduction row K-1 on the C-fragment layout
-        const double *xr = buf + (size_t)(K - 1) * NTP + ncol0 + 2 * (lane & 3);
+      if (XMODE == 2) {  // the reduction row K-1 on the C-fragment layout (operands fetched before the k loop)
 #pragma unroll
         for (int a = 0; a < QP; ++a) {
           if (ot0 + a < q) {
-            const double wk = wx[8 * (ot0 + a) + (lane >> 2)];
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) {
-              const double2 xin = *reinterpret_cast<const double2 *>(xr + 8 * nb);
-              acc[a][nb][0] = fma(wk, xin.x, acc[a][nb][0]);
-              acc[a][nb][1] = fma(wk, xin.y, acc[a][nb][1]);
+              acc[a][nb][0] = fma(wk2[a], xin2[nb].x, acc[a][nb][0]);
+              acc[a][nb][1] = fma(wk2[a], xin2[nb].y, acc[a][nb][1]);
             }
           }
         }

@@ -10,6 +10,7 @@
 // last pass.  Extra traffic: 32*N_m bytes, about 2 x 1.1 ms at BASELINE config 2, instead of the
 // 30-50 ms of the strided DFMA kernel.  EXACT mode keeps the bit-ordered DFMA kernel.
 #include "kb200_common.cuh"
+#include <algorithm>
 #include <map>
 #include <vector>
 
@@ -55,6 +56,80 @@ __global__ void __launch_bounds__(256) moments_transpose_kernel(const double *__
   }
 }
 
+// ZGD ([z][g][nm]): a zone's (group, moment) block is one contiguous run of Gs*M doubles, so a tile takes ZT zones x GH
+// groups: the moment-fastest side moves in runs of GH*M doubles (6.4 KB at config 2) and the zone-fastest side in rows of
+// ZT zones (128 bytes), instead of the 200-byte runs at a 12.8 KB stride the (group, 64 zones) tiles above would read
+// in this nesting (measured through the generic tiled transform: 3.2 TB/s for the four passes of a scattering call).
+constexpr int ZT = 16;
+struct ZgdChunk {  // one chunk pair of a batched launch (blockIdx.z)
+  const double *src;
+  double *dst;
+  long long accumulate;
+};
+template <bool TO_ZONE_FASTEST>
+__global__ void __launch_bounds__(256) moments_transpose_zgd_kernel(const ZgdChunk *__restrict__ chunks, int M, int Gs, int Zs, int GH) {
+  extern __shared__ double tsm[];            // [ZT][P]
+  const double *__restrict__ src = chunks[blockIdx.z].src;
+  double *__restrict__ dst = chunks[blockIdx.z].dst;
+  const int accumulate = chunks[blockIdx.z].accumulate;
+  const int X = GH * M, P = X | 1;           // odd pitch: the 16 zones of a row sit in 16 different bank pairs
+  const int z0 = blockIdx.x * ZT, g0 = blockIdx.y * GH;
+  const int nz = min(ZT, Zs - z0), ng = min(GH, Gs - g0), nx = ng * M;
+  const long long zf_sa = (long long)Gs * Zs;                      // zone-fastest side: nm * Gs*Zs + g * Zs + z
+  const long long mf_base = (long long)z0 * Gs * M + (long long)g0 * M;  // moment-fastest side: + zl * Gs*M + x
+  const int hl = threadIdx.x & 15, hw = threadIdx.x >> 4;          // 16 lanes per row, 16 rows per pass
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int U = 8;  // loads in flight per thread
+  if (TO_ZONE_FASTEST) {
+    for (int zl = warp; zl < nz; zl += 8) {  // a warp per zone: 256-byte pieces of the zone's run
+      const double *run = src + mf_base + (long long)zl * Gs * M;
+      double *row = tsm + zl * P;
+      for (int x0 = lane; x0 < nx; x0 += 32 * U) {
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = (x0 + 32 * u < nx) ? __ldg(run + x0 + 32 * u) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (x0 + 32 * u < nx) row[x0 + 32 * u] = v[u];
+      }
+    }
+    __syncthreads();
+    for (int x = hw; x < nx; x += 16) {
+      const int gl = x / M, nm = x - gl * M;
+      if (hl < nz) dst[(long long)nm * zf_sa + (long long)(g0 + gl) * Zs + z0 + hl] = tsm[hl * P + x];
+    }
+  } else {
+    for (int x0 = hw; x0 < nx; x0 += 16 * U) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int x = x0 + 16 * u, gl = x / M, nm = x - gl * M;
+        v[u] = (x < nx && hl < nz) ? __ldg(src + (long long)nm * zf_sa + (long long)(g0 + gl) * Zs + z0 + hl) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (x0 + 16 * u < nx) tsm[hl * P + x0 + 16 * u] = v[u];
+    }
+    __syncthreads();
+    for (int zl = warp; zl < nz; zl += 8) {
+      double *run = dst + mf_base + (long long)zl * Gs * M;
+      const double *row = tsm + zl * P;
+      if (accumulate) {
+        for (int x0 = lane; x0 < nx; x0 += 32 * U) {
+          double v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) v[u] = (x0 + 32 * u < nx) ? run[x0 + 32 * u] : 0.0;
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (x0 + 32 * u < nx) run[x0 + 32 * u] = v[u] + row[x0 + 32 * u];
+        }
+      } else {
+        for (int x = lane; x < nx; x += 32) run[x] = row[x];
+      }
+    }
+  }
+}
+
 // scratch chunks in the zone-fastest order, kept between calls (freed when the process ends)
 struct RowScratch {
   std::vector<double *> bufs;
@@ -96,7 +171,8 @@ int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, double source, 
   bool any_acc = false;
   for (int i = 0; i < n; ++i) any_acc |= (h[i].accumulate != 0);
   if (any_acc && (layout == 1 || layout == 4)) return -1;
-  const bool generic = !any_acc;
+  const bool zgd = layout == 5 && !(getenv("KB200_ZGD_TRANSPOSE") && getenv("KB200_ZGD_TRANSPOSE")[0] == '0');
+  const bool generic = !any_acc && !zgd;
   const char *env = getenv("KB200_SCATTER_DFMA");
   if (env && env[0] == '1') return -1;
   const int M = h[0].M, Gs = h[0].Gs, Zs = h[0].Zs;
@@ -113,9 +189,36 @@ int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, double source, 
   if (rc) return rc;
   const Strides3 ms = strides_dgz(layout, M, Gs, Zs);  // the moment-fastest side: ms.a == 1
   const size_t smem = (size_t)TRZ * (M | 1) * sizeof(double);
-  if (smem > 48 * 1024) return -1;
+  if (!zgd && !generic) {
+    if (smem > 200 * 1024) return -1;
+    KB_CUDA(cudaFuncSetAttribute(moments_transpose_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KB_CUDA(cudaFuncSetAttribute(moments_transpose_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   const dim3 grid((Zs + TRZ - 1) / TRZ, Gs, 1);
+  // ZGD tiles: ZT zones x GH groups, GH chosen so that two blocks fit an SM
+  int GH = Gs;
+  while ((size_t)ZT * ((GH * M) | 1) * sizeof(double) > 54 * 1024 && GH > 1) GH = (GH + 1) / 2;  // four blocks per SM
+  const size_t zsmem = (size_t)ZT * ((GH * M) | 1) * sizeof(double);
+  const dim3 zgrid((Zs + ZT - 1) / ZT, (Gs + GH - 1) / GH, 1);
+  if (zgd) {
+    KB_CUDA(cudaFuncSetAttribute(moments_transpose_zgd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
+    KB_CUDA(cudaFuncSetAttribute(moments_transpose_zgd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
+  }
+  if (zgd) {  // all source chunks in one launch
+    std::vector<ZgdChunk> zc;
+    for (auto &kv : src_index) zc.push_back(ZgdChunk{kv.first, bufs[kv.second], 0});
+    const void *dz = nullptr;
+    rc = device_descs(zc.data(), zc.size() * sizeof(ZgdChunk), &dz, st);
+    if (rc) return rc;
+    for (size_t c0 = 0; c0 < zc.size(); c0 += 65535) {
+      const unsigned nc = (unsigned)std::min<size_t>(65535, zc.size() - c0);
+      moments_transpose_zgd_kernel<true><<<dim3(zgrid.x, zgrid.y, nc), 256, zsmem, st>>>((const ZgdChunk *)dz + c0, M, Gs, Zs, GH);
+      rc = post_launch("moments_transpose_zgd");
+      if (rc) return rc;
+    }
+  }
   for (auto &kv : src_index) {
+    if (zgd) break;
     if (generic) {
       rc = kb200_layout_transform(layout, 0, M, Gs, Zs, kv.first, bufs[kv.second], st);
     } else {
@@ -136,6 +239,20 @@ int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, double source, 
   if (rc) return rc;
   rc = kb200_scatter_mma_try(t.data(), n, d, layout, source, st);
   if (rc != 0) return rc < 0 ? -1 : rc;
+  if (zgd) {  // all destination chunks in one launch
+    std::vector<ZgdChunk> zc;
+    for (int i = 0; i < n; ++i) zc.push_back(ZgdChunk{bufs[nsrc + i], h[i].phi_out, h[i].accumulate});
+    const void *dz = nullptr;
+    rc = device_descs(zc.data(), zc.size() * sizeof(ZgdChunk), &dz, st);
+    if (rc) return rc;
+    for (size_t c0 = 0; c0 < zc.size(); c0 += 65535) {
+      const unsigned nc = (unsigned)std::min<size_t>(65535, zc.size() - c0);
+      moments_transpose_zgd_kernel<false><<<dim3(zgrid.x, zgrid.y, nc), 256, zsmem, st>>>((const ZgdChunk *)dz + c0, M, Gs, Zs, GH);
+      rc = post_launch("moments_transpose_zgd");
+      if (rc) return rc;
+    }
+    return 0;
+  }
   for (int i = 0; i < n; ++i) {
     if (generic) {
       rc = kb200_layout_transform(0, layout, M, Gs, Zs, bufs[nsrc + i], h[i].phi_out, st);
