@@ -680,6 +680,10 @@ class BlockJacobiComm : public ParallelComm {
 
 // ---- solvers: src/Kripke/SweepSolver.h:20-22, SteadyStateSolver.h:18 -----------------------------------------------
 void SweepSolver(Core::DataStore &data_store, std::vector<SdomId> subdomain_list, bool block_jacobi);
+// the wavefront schedule SweepSolver runs (also what kripke_b200_sweep_schedule reports): depth of a local subdomain in the
+// sweep DAG of its octant over the GLOBAL zone-set grid, and the number of global stages
+int sweepDepth(Core::DataStore &data_store, Core::PartitionSpace const &pspace, SdomId local);
+int numStages(Core::PartitionSpace const &pspace);
 int SteadyStateSolver(Core::DataStore &data_store, size_t max_iter, bool block_jacobi);
 // per-iteration particle counts of the last SteadyStateSolver call (full precision; stdout only has %e)
 std::vector<double> const &lastParticleCounts();

@@ -127,21 +127,12 @@ int kripke_b200_sweep_schedule(void *hv, int *order, int *stage, int *recv_from,
   const int n = (int)pspace.getNumSubdomains(SPACE_PQR);
   auto &f_up = ds.getVariable<Field_Adjacency>("upwind");
   auto &f_down = ds.getVariable<Field_Adjacency>("downwind");
-  const int nstages = (int)(pspace.getGlobalNumSubdomains(SPACE_RX) + pspace.getGlobalNumSubdomains(SPACE_RY) +
-                            pspace.getGlobalNumSubdomains(SPACE_RZ)) - 2;
+  const int nstages = numStages(pspace);  // the planner of host/sweep_solver.cpp, not a copy of it
   int k = 0;
   for (int st = 0; st < nstages; ++st)
     for (int s = 0; s < n; ++s) {
       SdomId sdom(s);
-      auto gc = pspace.coordToGlobalCoord(pspace.sdomIdToCoord(sdom));
-      const int dir[3] = {ds.getVariable<Field_Direction2Int>("quadrature/id").getDataConst(sdom)[0],
-                          ds.getVariable<Field_Direction2Int>("quadrature/jd").getDataConst(sdom)[0],
-                          ds.getVariable<Field_Direction2Int>("quadrature/kd").getDataConst(sdom)[0]};
-      int depth = 0;
-      for (int dim = 0; dim < 3; ++dim) {
-        const long nn = (long)pspace.getGlobalNumSubdomains((SPACE)(SPACE_RX + dim));
-        depth += (dir[dim] > 0) ? (int)gc[SPACE_RX + dim] : (int)(nn - 1 - gc[SPACE_RX + dim]);
-      }
+      int depth = sweepDepth(ds, pspace, sdom);
       if (h->vars.parallel_method == PMETHOD_BJ) depth = 0;
       if (depth != st) continue;
       order[k] = s;

@@ -22,13 +22,8 @@
 using namespace Kripke;
 using namespace Kripke::Core;
 
-namespace {
-
-bool referenceOrder() {
-  const char *e = getenv("KB200_SWEEP_ORDER");
-  return e && !strcasecmp(e, "reference");
-}
-
+namespace Kripke {
+// (declared in Kripke.h: the C API's schedule query and the solver below share these)
 // depth of a global subdomain in the sweep DAG of its octant
 int sweepDepth(DataStore &ds, PartitionSpace const &pspace, SdomId local) {
   auto gc = pspace.coordToGlobalCoord(pspace.sdomIdToCoord(local));
@@ -46,6 +41,14 @@ int sweepDepth(DataStore &ds, PartitionSpace const &pspace, SdomId local) {
 int numStages(PartitionSpace const &pspace) {
   return (int)(pspace.getGlobalNumSubdomains(SPACE_RX) + pspace.getGlobalNumSubdomains(SPACE_RY) +
                pspace.getGlobalNumSubdomains(SPACE_RZ)) - 2;
+}
+}  // namespace Kripke
+
+namespace {
+
+bool referenceOrder() {
+  const char *e = getenv("KB200_SWEEP_ORDER");
+  return e && !strcasecmp(e, "reference");
 }
 
 struct Message {
