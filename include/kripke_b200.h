@@ -88,6 +88,8 @@ typedef struct {
   double *phi;                          /* [M x Gs x Zs] in `layout` order */
 } kb200_ltimes_desc;
 int kb200_ltimes(const kb200_ltimes_desc *h_descs, int n, kb200_stream_t stream);
+/* launches of the producer/consumer-group LTimes kernel (kb200_moments_slab.cu: M = 25, zone- or group-fastest columns) so far */
+unsigned long long kb200_ltimes_slab_launches(void);
 
 /* ---- LPlusTimes: Kripke::Kernel::LPlusTimes (src/Kripke/Kernel/LPlusTimes.cpp:68-92, body :49-60)
  * rhs_q(d,g,z) (+)= sum_nm ell_plus_q(d,nm) * phi_out(nm,g,z) for each direction-set chunk q.

@@ -284,7 +284,7 @@ struct MomentsDescK {
 using namespace kb200;
 
 int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, int nsets, int accumulate, const void *d_views,
-                          int n, const void *const *h_ptrs, int n_ptrs, cudaStream_t st);  // kb200_moments_mma.cu
+                          int n, const void *const *h_ptrs, int n_ptrs, int same_w, cudaStream_t st);  // kb200_moments_mma.cu
 int kb200_moments_rowmma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, int nsets, int accumulate, const void *d_views,
                              int n, const void *const *h_ptrs, int n_ptrs, cudaStream_t st);  // kb200_moments_rowmma.cu
 
@@ -373,7 +373,13 @@ static int run_moments(int mode, int layout, int M, int Ds, int Gs, int Zs, int 
       for (int s = 0; s < (mode == 0 ? nsets : 1); ++s) ptrs.push_back(tin[s]);
       for (int s = 0; s < (mode == 0 ? 1 : nsets); ++s) ptrs.push_back(tout[s]);
     }
-    rc = kb200_moments_mma_try(mode, layout, M, Ds, Gs, Zs, nsets, accumulate, d_views, n, ptrs.data(), (int)ptrs.size(), st);
+    int same_w = 1;  // every descriptor of the call uses the same weight tables (true for the host layer: one ell per direction set)
+    for (int i = 1; i < n && same_w; ++i) {
+      const void *const *w0 = (const void *const *)((const char *)h_descs + off_w);
+      const void *const *wi = (const void *const *)((const char *)h_descs + desc_stride * i + off_w);
+      for (int s = 0; s < nsets; ++s) same_w = same_w && (w0[s] == wi[s]);
+    }
+    rc = kb200_moments_mma_try(mode, layout, M, Ds, Gs, Zs, nsets, accumulate, d_views, n, ptrs.data(), (int)ptrs.size(), same_w, st);
     if (rc >= 0) return rc;
     rc = kb200_moments_rowmma_try(mode, layout, M, Ds, Gs, Zs, nsets, accumulate, d_views, n, ptrs.data(), (int)ptrs.size(), st);
     if (rc >= 0) return rc;

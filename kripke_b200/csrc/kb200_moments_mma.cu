@@ -419,8 +419,12 @@ static int launch_mma(const MomentsDescK *d_views, int n, const MmaGeom &gm, cud
 }
 
 // Returns 0 if handled, -1 if this path does not apply (caller falls back to the DFMA kernels), >0 on error.
+int kb200_ltimes_slab_try(int M, int Ds, int nsets, int accumulate, long long B, long long N, long long in_b, long long in_r,
+                          long long out_b, long long out_r, const void *d_views, int n, const void *const *h_ptrs, int same_w,
+                          cudaStream_t st);  // kb200_moments_slab.cu
+
 int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, int nsets, int accumulate, const void *d_views,
-                          int n, const void *const *h_ptrs, int n_ptrs, cudaStream_t st) {
+                          int n, const void *const *h_ptrs, int n_ptrs, int same_w, cudaStream_t st) {
   if (layout != 0 && layout != 1 && layout != 2 && layout != 4) return -1;
   const char *env = getenv("KB200_MOMENTS_DFMA");
   if (env && env[0] == '1') return -1;
@@ -453,6 +457,11 @@ int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, i
     gm.npass = 1;
     gm.ntn = (gm.N + 127) / 128;
     if (gm.q == 4 && gm.O == 25) {  // 3 tensor-core tiles + one DFMA row instead of 4 tiles (22% less fp64 work)
+      if (mode == 0 && gm.pack_N == 0 && n_ptrs == n * (nsets + 1)) {  // producer warps + consumer groups (kb200_moments_slab.cu)
+        const int rc = kb200_ltimes_slab_try(M, Ds, nsets, accumulate, gm.B, gm.N, gm.in_b, gm.in_r, gm.out_b, gm.out_r, d_views, n, h_ptrs,
+                                             same_w, st);
+        if (rc != -1) return rc;
+      }
       gm.q = 3;
       const char *e = getenv("KB200_LTIMES_KC");
       const int kc = e ? atoi(e) : 32;

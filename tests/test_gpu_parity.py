@@ -86,10 +86,15 @@ def test_moments_tensor_core_shapes(gpu, shape, layout):
     L, quad = MOMENT_SHAPES[shape]
     args = f"--zones 10,6,8 --groups 6 --quad {quad} --legendre {L} --gset 2 --dset 8 --zset 1,2,1 --layout {layout}"
     p, o, _, _ = pair(gpu, args)
+    A = gpu.abi()
+    A.kb200_ltimes_slab_launches.restype = C.c_ulonglong
+    slab0 = A.kb200_ltimes_slab_launches()
     fill_both(p, o, "psi", 1100 + shape, -1.0, 2.0)
     o.zero("phi"); o.ltimes()
     p.call("zero:phi"); p.call("LTimes")
     assert_close(p.field("phi"), o.field("phi"), f"LTimes L={L} {layout}", False)
+    # M = 25 with contiguous (group, zone) columns runs on the producer/consumer-group kernel of kb200_moments_slab.cu
+    assert (A.kb200_ltimes_slab_launches() > slab0) == (L == 4 and layout in ("DGZ", "DZG", "GDZ")), (L, layout)
     fill_both(p, o, "phi_out", 1200 + shape, -1.0, 1.0)
     o.zero("rhs"); o.lplustimes()
     p.call("zero:rhs"); p.call("LPlusTimes")
