@@ -15,6 +15,10 @@
 // * an accumulator lane ends up with four consecutive columns of a moment row = one 32-byte store.
 // Tiles are flattened over the descriptors of a call (phi chunks), so many small chunks still fill every SM evenly.
 // Anything it does not cover returns -1 and moments_mma_kernel runs instead.
+// (LPlusTimes was tried in the same structure -- B fragments of a warp's 16 columns in registers, direction blocks in pairs,
+// 32-byte stores -- and measured 7.1 ms against the 6.2 ms of moments_mma_kernel at config 2: that kernel is bound by its
+// 25.7 GB store stream, ncu showed the warps waiting on store-data registers, and 512-byte row pieces written by four
+// warps at their own pace drain more slowly than the older kernel's 1 KB pieces; profiles/r02bf_*.  It was removed again.)
 #include <vector>
 #include "kb200_common.cuh"
 
@@ -27,7 +31,7 @@ struct MomentsDescK {  // same as in kb200_moments.cu
 };
 
 struct MsGeom {
-  int M, Ds, K, nkc4, nst, accumulate;
+  int M, Ds, K, nkc4, nst, accumulate, adj;
   int ntn, per_desc, ntiles;  // column tiles per batch, tiles per descriptor, tiles of the call
   long long N, in_b, out_b;   // columns per batch; batch strides of psi and phi
 };
@@ -99,7 +103,8 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ltimes_slab_kernel(const Moment
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
-  const int first = (int)blockIdx.x + grp * (int)gridDim.x, step = MS_NG * (int)gridDim.x;  // this group's tiles
+  // this group's tiles: the groups of a CTA work on neighbouring tiles (KB200_MS_ADJ=1; default: a grid apart, measured equal or better)
+  const int first = gm.adj ? MS_NG * (int)blockIdx.x + grp : (int)blockIdx.x + grp * (int)gridDim.x, step = MS_NG * (int)gridDim.x;
   if (warp >= NW) {
     // ---- producer of group grp: one bulk copy per direction row of a stage ----
     unsigned it = 0;
@@ -190,6 +195,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ltimes_slab_kernel(const Moment
   }
 }
 
+
 }  // namespace kb200
 
 using namespace kb200;
@@ -216,6 +222,7 @@ int kb200_ltimes_slab_try(int M, int Ds, int nsets, int accumulate, long long B,
   memset(&gm, 0, sizeof(gm));
   gm.M = M; gm.Ds = Ds; gm.K = K; gm.nkc4 = nkc4; gm.nst = nst; gm.accumulate = accumulate;
   gm.N = N; gm.in_b = in_b; gm.out_b = out_b;
+  { const char *ae = getenv("KB200_MS_ADJ"); gm.adj = (ae && ae[0] == '1'); }
   const long long ntn = (N + MS_NT - 1) / MS_NT;
   if (ntn * B * n > 0x3fffffffLL) return -1;
   gm.ntn = (int)ntn; gm.per_desc = (int)(ntn * B); gm.ntiles = gm.per_desc * n;

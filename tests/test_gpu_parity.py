@@ -102,6 +102,8 @@ def test_moments_tensor_core_shapes(gpu, shape, layout):
     # accumulate semantics (no pending zero-fill): a second call adds on top
     o.ltimes(); p.call("LTimes")
     assert_close(p.field("phi"), o.field("phi"), f"LTimes accumulate L={L} {layout}", False)
+    o.lplustimes(); p.call("LPlusTimes")
+    assert_close(p.field("rhs"), o.field("rhs"), f"LPlusTimes accumulate L={L} {layout}", False)
 
 
 @pytest.mark.parametrize("exact", [False, True])

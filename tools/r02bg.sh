@@ -1,0 +1,4 @@
+timeout 300 python -X faulthandler -m pytest tests -m gpu -x -q -k "lplustimes or moments or golden" 2>&1 | tail -3
+for e in 1 0; do echo KB200_LPLUSTIMES_SLAB=$e; for c in config2:DGZ config4:DGZ config5:DGZ; do
+  KB200_LPLUSTIMES_SLAB=$e timeout 60 python tools/gpu_probe.py $c 2>&1 | grep -E "config|LPlusTimes"
+done; done | tee gpurun_out/r02bg_probe.log
