@@ -60,15 +60,16 @@ __global__ void __launch_bounds__(256) moments_transpose_kernel(const double *__
 // groups: the moment-fastest side moves in runs of GH*M doubles (6.4 KB at config 2) and the zone-fastest side in rows of
 // ZT zones (128 bytes), instead of the 200-byte runs at a 12.8 KB stride the (group, 64 zones) tiles above would read
 // in this nesting (measured through the generic tiled transform: 3.2 TB/s for the four passes of a scattering call).
-constexpr int ZT = 16;
+// ZT = 64 (512-byte rows on the zone-fastest side) or 16.
 struct ZgdChunk {  // one chunk pair of a batched launch (blockIdx.z)
   const double *src;
   double *dst;
   long long accumulate;
 };
-template <bool TO_ZONE_FASTEST>
+template <bool TO_ZONE_FASTEST, int ZT>
 __global__ void __launch_bounds__(256) moments_transpose_zgd_kernel(const ZgdChunk *__restrict__ chunks, int M, int Gs, int Zs, int GH) {
   extern __shared__ double tsm[];            // [ZT][P]
+  constexpr int RL = ZT < 32 ? ZT : 32, PPR = ZT / RL, RPP = 256 / RL;  // lanes per row piece, pieces per row, pieces per pass
   const double *__restrict__ src = chunks[blockIdx.z].src;
   double *__restrict__ dst = chunks[blockIdx.z].dst;
   const int accumulate = chunks[blockIdx.z].accumulate;
@@ -77,13 +78,27 @@ __global__ void __launch_bounds__(256) moments_transpose_zgd_kernel(const ZgdChu
   const int nz = min(ZT, Zs - z0), ng = min(GH, Gs - g0), nx = ng * M;
   const long long zf_sa = (long long)Gs * Zs;                      // zone-fastest side: nm * Gs*Zs + g * Zs + z
   const long long mf_base = (long long)z0 * Gs * M + (long long)g0 * M;  // moment-fastest side: + zl * Gs*M + x
-  const int hl = threadIdx.x & 15, hw = threadIdx.x >> 4;          // 16 lanes per row, 16 rows per pass
+  const int hl = threadIdx.x % RL, hw = threadIdx.x / RL;          // lane inside a row piece, piece of the pass
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int U = 8;  // loads in flight per thread
+  // every zone's run starts on a 16-byte boundary and holds an even number of doubles
+  const bool vec2 = ((Gs * M) % 2 == 0) && ((GH * M) % 2 == 0) && (nx % 2 == 0) && ((reinterpret_cast<uintptr_t>(TO_ZONE_FASTEST ? (const void *)src : (const void *)dst) & 15) == 0);
   if (TO_ZONE_FASTEST) {
-    for (int zl = warp; zl < nz; zl += 8) {  // a warp per zone: 256-byte pieces of the zone's run
+    for (int zl = warp; zl < nz; zl += 8) {  // a warp per zone: 512-byte (or 256-byte) pieces of the zone's run
       const double *run = src + mf_base + (long long)zl * Gs * M;
       double *row = tsm + zl * P;
+      if (vec2) {  // 16-byte loads: twice the bytes in flight per thread
+        const double2 *run2 = reinterpret_cast<const double2 *>(run);
+        for (int x0 = lane; x0 < nx / 2; x0 += 32 * U) {
+          double2 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) v[u] = (x0 + 32 * u < nx / 2) ? __ldg(run2 + x0 + 32 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (x0 + 32 * u < nx / 2) { row[2 * (x0 + 32 * u)] = v[u].x; row[2 * (x0 + 32 * u) + 1] = v[u].y; }
+        }
+        continue;
+      }
       for (int x0 = lane; x0 < nx; x0 += 32 * U) {
         double v[U];
 #pragma unroll
@@ -94,21 +109,23 @@ __global__ void __launch_bounds__(256) moments_transpose_zgd_kernel(const ZgdChu
       }
     }
     __syncthreads();
-    for (int x = hw; x < nx; x += 16) {
-      const int gl = x / M, nm = x - gl * M;
-      if (hl < nz) dst[(long long)nm * zf_sa + (long long)(g0 + gl) * Zs + z0 + hl] = tsm[hl * P + x];
+    for (int pi = hw; pi < nx * PPR; pi += RPP) {
+      const int x = pi / PPR, zl = (pi - x * PPR) * RL + hl, gl = x / M, nm = x - gl * M;
+      if (zl < nz) dst[(long long)nm * zf_sa + (long long)(g0 + gl) * Zs + z0 + zl] = tsm[zl * P + x];
     }
   } else {
-    for (int x0 = hw; x0 < nx; x0 += 16 * U) {
+    for (int p0 = hw; p0 < nx * PPR; p0 += RPP * U) {
       double v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int x = x0 + 16 * u, gl = x / M, nm = x - gl * M;
-        v[u] = (x < nx && hl < nz) ? __ldg(src + (long long)nm * zf_sa + (long long)(g0 + gl) * Zs + z0 + hl) : 0.0;
+        const int pi = p0 + RPP * u, x = pi / PPR, zl = (pi - x * PPR) * RL + hl, gl = x / M, nm = x - gl * M;
+        v[u] = (pi < nx * PPR && zl < nz) ? __ldg(src + (long long)nm * zf_sa + (long long)(g0 + gl) * Zs + z0 + zl) : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (x0 + 16 * u < nx) tsm[hl * P + x0 + 16 * u] = v[u];
+      for (int u = 0; u < U; ++u) {
+        const int pi = p0 + RPP * u, x = pi / PPR, zl = (pi - x * PPR) * RL + hl;
+        if (pi < nx * PPR) tsm[zl * P + x] = v[u];
+      }
     }
     __syncthreads();
     for (int zl = warp; zl < nz; zl += 8) {
@@ -123,6 +140,9 @@ __global__ void __launch_bounds__(256) moments_transpose_zgd_kernel(const ZgdChu
           for (int u = 0; u < U; ++u)
             if (x0 + 32 * u < nx) run[x0 + 32 * u] = v[u] + row[x0 + 32 * u];
         }
+      } else if (vec2) {
+        double2 *run2 = reinterpret_cast<double2 *>(run);
+        for (int x = lane; x < nx / 2; x += 32) run2[x] = make_double2(row[2 * x], row[2 * x + 1]);
       } else {
         for (int x = lane; x < nx; x += 32) run[x] = row[x];
       }
@@ -195,14 +215,19 @@ int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, double source, 
     KB_CUDA(cudaFuncSetAttribute(moments_transpose_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   const dim3 grid((Zs + TRZ - 1) / TRZ, Gs, 1);
-  // ZGD tiles: ZT zones x GH groups, GH chosen so that two blocks fit an SM
+  // ZGD tiles: ZT zones x GH groups, sized so that four blocks fit an SM (KB200_ZGD_ZT=64: 512-byte rows on the zone-fastest side)
+  int ZT = 16;  // measured at config 2: 5.69 ms per scattering call with 16 zones per tile, 5.92 ms with 64
+  { const char *ze = getenv("KB200_ZGD_ZT"); if (ze && atoi(ze) == 64) ZT = 64; }
+  if ((size_t)ZT * (M | 1) * sizeof(double) > 54 * 1024 || Zs < 64) ZT = 16;
   int GH = Gs;
-  while ((size_t)ZT * ((GH * M) | 1) * sizeof(double) > 54 * 1024 && GH > 1) GH = (GH + 1) / 2;  // four blocks per SM
+  while ((size_t)ZT * ((GH * M) | 1) * sizeof(double) > 54 * 1024 && GH > 1) GH = (GH + 1) / 2;
   const size_t zsmem = (size_t)ZT * ((GH * M) | 1) * sizeof(double);
   const dim3 zgrid((Zs + ZT - 1) / ZT, (Gs + GH - 1) / GH, 1);
   if (zgd) {
-    KB_CUDA(cudaFuncSetAttribute(moments_transpose_zgd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
-    KB_CUDA(cudaFuncSetAttribute(moments_transpose_zgd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
+    KB_CUDA(cudaFuncSetAttribute(moments_transpose_zgd_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
+    KB_CUDA(cudaFuncSetAttribute(moments_transpose_zgd_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
+    KB_CUDA(cudaFuncSetAttribute(moments_transpose_zgd_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
+    KB_CUDA(cudaFuncSetAttribute(moments_transpose_zgd_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
   }
   if (zgd) {  // all source chunks in one launch
     std::vector<ZgdChunk> zc;
@@ -212,7 +237,8 @@ int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, double source, 
     if (rc) return rc;
     for (size_t c0 = 0; c0 < zc.size(); c0 += 65535) {
       const unsigned nc = (unsigned)std::min<size_t>(65535, zc.size() - c0);
-      moments_transpose_zgd_kernel<true><<<dim3(zgrid.x, zgrid.y, nc), 256, zsmem, st>>>((const ZgdChunk *)dz + c0, M, Gs, Zs, GH);
+      if (ZT == 64) moments_transpose_zgd_kernel<true, 64><<<dim3(zgrid.x, zgrid.y, nc), 256, zsmem, st>>>((const ZgdChunk *)dz + c0, M, Gs, Zs, GH);
+      else moments_transpose_zgd_kernel<true, 16><<<dim3(zgrid.x, zgrid.y, nc), 256, zsmem, st>>>((const ZgdChunk *)dz + c0, M, Gs, Zs, GH);
       rc = post_launch("moments_transpose_zgd");
       if (rc) return rc;
     }
@@ -247,7 +273,8 @@ int kb200_scatter_row_try(const kb200_scattering_desc *h, int n, double source, 
     if (rc) return rc;
     for (size_t c0 = 0; c0 < zc.size(); c0 += 65535) {
       const unsigned nc = (unsigned)std::min<size_t>(65535, zc.size() - c0);
-      moments_transpose_zgd_kernel<false><<<dim3(zgrid.x, zgrid.y, nc), 256, zsmem, st>>>((const ZgdChunk *)dz + c0, M, Gs, Zs, GH);
+      if (ZT == 64) moments_transpose_zgd_kernel<false, 64><<<dim3(zgrid.x, zgrid.y, nc), 256, zsmem, st>>>((const ZgdChunk *)dz + c0, M, Gs, Zs, GH);
+      else moments_transpose_zgd_kernel<false, 16><<<dim3(zgrid.x, zgrid.y, nc), 256, zsmem, st>>>((const ZgdChunk *)dz + c0, M, Gs, Zs, GH);
       rc = post_launch("moments_transpose_zgd");
       if (rc) return rc;
     }

@@ -337,6 +337,59 @@ def test_layout_transform_round_trip(gpu):
         A.kb200_free(b)
 
 
+class _LTimesDesc(C.Structure):  # kb200_ltimes_desc (include/kripke_b200.h)
+    _fields_ = [("layout", C.c_int), ("M", C.c_int), ("Ds", C.c_int), ("Gs", C.c_int), ("Zs", C.c_int), ("nsets", C.c_int),
+                ("accumulate", C.c_int), ("ell", C.c_void_p * 64), ("psi", C.c_void_p * 64), ("phi", C.c_void_p)]
+
+
+@pytest.mark.parametrize("shared_ell, zs", [(True, 96), (False, 96), (True, 90)])
+def test_ltimes_abi_slab_kernel_and_its_fallbacks(gpu, shared_ell, zs):
+    """kb200_ltimes straight through the C ABI at M = 25 (DGZ), two phi chunks x two direction sets, against numpy:
+    chunks that share their ell tables run on kb200_moments_slab.cu; different tables per chunk, or a column count that is
+    not a multiple of four, must be declined by it and served by the per-chunk kernel -- all with the same result."""
+    A = gpu.abi()
+    A.kb200_ltimes_slab_launches.restype = C.c_ulonglong
+    A.kb200_ltimes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    M, Ds, Gs, nsets, nchunk = 25, 12, 3, 2, 2
+    rng = np.random.default_rng(77)
+    held = []
+
+    def dev(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        p = C.c_void_p()
+        assert A.kb200_alloc(a.nbytes, C.byref(p)) == 0
+        A.kb200_upload(p, a.ctypes.data_as(C.c_void_p), a.nbytes, None)
+        held.append(p)
+        return p
+
+    ells = [[rng.uniform(-1, 1, (Ds, M)) for _ in range(nsets)] for _ in range(1 if shared_ell else nchunk)]
+    d_ells = [[dev(e) for e in es] for es in ells]
+    descs = (_LTimesDesc * nchunk)()
+    expect, d_phi = [], []
+    for c in range(nchunk):
+        es, des = (ells[0], d_ells[0]) if shared_ell else (ells[c], d_ells[c])
+        psis = [rng.uniform(-1, 2, (Ds, Gs, zs)) for _ in range(nsets)]
+        phi0 = rng.uniform(-1, 1, (M, Gs, zs))
+        d = descs[c]
+        d.layout, d.M, d.Ds, d.Gs, d.Zs, d.nsets, d.accumulate = 0, M, Ds, Gs, zs, nsets, 1
+        for q in range(nsets):
+            d.ell[q] = des[q].value
+            d.psi[q] = dev(psis[q]).value
+        d_phi.append(dev(phi0))
+        d.phi = d_phi[-1].value
+        expect.append(phi0 + sum(np.einsum("dm,dgz->mgz", es[q], psis[q]) for q in range(nsets)))
+    before = A.kb200_ltimes_slab_launches()
+    assert A.kb200_ltimes(C.byref(descs), nchunk, None) == 0
+    assert (A.kb200_ltimes_slab_launches() > before) == (shared_ell and (Gs * zs) % 4 == 0)
+    for c in range(nchunk):
+        out = np.empty((M, Gs, zs))
+        A.kb200_download(out.ctypes.data_as(C.c_void_p), d_phi[c], out.nbytes, None)
+        A.kb200_stream_sync(None)
+        assert_close(out, expect[c], f"kb200_ltimes chunk {c}", False)
+    for p in held:
+        A.kb200_free(p)
+
+
 def test_fused_population_abi_matches_separate_kernel(gpu):
     """kb200_sweep_population + kb200_population_reduce (sum left behind by the sweep) == kb200_population on the
     same psi, and the host layer falls back to the separate kernel as soon as psi is written by anyone else."""

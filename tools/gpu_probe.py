@@ -21,6 +21,21 @@ def main():
     A.kb200_peak_fp64_gflops(0, 4000, C.byref(g)); out["dfma_gflops"] = g.value
     A.kb200_peak_fp64_gflops(1, 4000, C.byref(g)); out["dmma_gflops"] = g.value
     A.kb200_peak_copy_gbs(4 << 30, 5, C.byref(g)); out["copy_gbs"] = g.value
+    # write-only stream (kb200_fill_f64 over 8 GB): what a store-dominated kernel such as LPlusTimes can hope for
+    buf, e0, e1, ms = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_float()
+    nfill = 1 << 30
+    if A.kb200_alloc(nfill * 8, C.byref(buf)) == 0:
+        A.kb200_event_create(C.byref(e0)); A.kb200_event_create(C.byref(e1))
+        best = 1e30
+        for _ in range(4):
+            A.kb200_event_record(e0, None)
+            A.kb200_fill_f64(buf, 1.0, nfill, None)
+            A.kb200_event_record(e1, None)
+            A.kb200_event_sync(e1)
+            A.kb200_event_elapsed_ms(e0, e1, C.byref(ms))
+            best = min(best, ms.value)
+        out["fill_gbs"] = nfill * 8 / (best * 1e-3) * 1e-9
+        A.kb200_free(buf)
     print(json.dumps(out), flush=True)
     pairs = sys.argv[1:] or ["small:DGZ", "small:GZD", "small:ZGD"]
     kernels = ["LTimes", "scattering", "source", "LPlusTimes", "SweepSolver", "population"]
