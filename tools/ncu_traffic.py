@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ENTRY = [("sweep_", "SweepSolver"), ("p2p_", "SweepSolver_sync"), ("moments_mma_kernel<3", "LTimes"), ("moments_mma_kernel<4", "LPlusTimes"),
-         ("moments_rowmma_stream", "LTimes"), ("moments_rowmma_resident", "LPlusTimes"), ("scatter_slab", "scattering"), ("scatter_mma", "scattering"),
+         ("ltimes_slab", "LTimes"), ("moments_rowmma_stream", "LTimes"), ("moments_rowmma_resident", "LPlusTimes"), ("scatter_slab", "scattering"), ("scatter_mma", "scattering"),
          ("scatter_fractions", "scattering_fractions"), ("slab_fractions", "scattering_fractions"), ("slab_matrices", "scattering_matrices"), ("moments_transpose", "scattering_transpose"), ("population", "population"), ("source", "source")]
 
 

@@ -16,7 +16,7 @@ for lay in GZD ZGD; do
 done
 #timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_reference_arm.json 2>> $O/${TAG}_bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_config2_DGZ.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'sweep_|moments_|scatter_|population' --launch-skip 6 -c 6 -o /tmp/${TAG}_full_config2_DGZ python tools/gpu_probe.py config2:DGZ > $O/${TAG}_full_dgz.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'sweep_|moments_|ltimes_slab|scatter_|population' --launch-skip 6 -c 6 -o /tmp/${TAG}_full_config2_DGZ python tools/gpu_probe.py config2:DGZ > $O/${TAG}_full_dgz.log 2>&1
 python tools/ncu_summary.py /tmp/${TAG}_full_config2_DGZ.ncu-rep > $O/${TAG}_ncu_full_config2_DGZ_summary.txt 2>&1
 python tools/ncu_traffic.py /tmp/${TAG}_full_config2_DGZ.ncu-rep config2:DGZ $O/${TAG}_ncu_traffic.json $COMMIT > /dev/null 2>&1
 python tools/ncu_opcodes.py /tmp/${TAG}_full_config2_DGZ.ncu-rep 30 > $O/${TAG}_ncu_opcodes_config2_DGZ_first_kernel.txt 2>&1
