@@ -284,6 +284,11 @@ __global__ void __launch_bounds__(32 * (WO * WN + 1) * NG, 1) scatter_slab_kerne
           const double2 u = sl_lds128(fa), v = sl_lds128(fa + 16u);
           sx[0] = gm.source * u.x; sx[1] = gm.source * u.y; sx[2] = gm.source * v.x; sx[3] = gm.source * v.y;
         }
+        // hand the stage back: every lane's shared loads above are ordered before lane 0's arrive (release) by the warp
+        // barrier, and the producer's refill is ordered after its wait (acquire) on the same mbarrier.  compute-sanitizer's
+        // racecheck still reports a "potential WAR hazard" between a lane != 0 and the refill, because that lane does not
+        // arrive itself (profiles/r02bl_racecheck.log); one arrival per lane would cost 32 serialised shared atomics per warp
+        // and stage.  memcheck is clean (profiles/r02bl_memcheck.log).
         __syncwarp();
         if (lane == 0) sl_mb_arrive(empty0 + 8u * s);
       }
