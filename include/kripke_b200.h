@@ -101,6 +101,8 @@ typedef struct {
   double *rhs[KB200_MAX_DIRSETS];            /* [Ds x Gs x Zs] each */
 } kb200_lplustimes_desc;
 int kb200_lplustimes(const kb200_lplustimes_desc *h_descs, int n, kb200_stream_t stream);
+/* launches so far of the producer/consumer-group kernel as a plain product (M >= 36, DGZ/DZG, outputs a multiple of 32) */
+unsigned long long kb200_lplustimes_slab_launches(void);
 
 /* ---- Scattering: Kripke::Kernel::scattering (src/Kripke/Kernel/Scattering.cpp:112-164, body :73-99)
  * For one zone set R and one destination group set: phi_out(nm,g,z) (+)= sum over the `nsrc`

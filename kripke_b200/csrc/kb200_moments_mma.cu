@@ -423,6 +423,9 @@ int kb200_ltimes_slab_try(int M, int Ds, int nsets, int accumulate, long long B,
                           long long out_b, long long out_r, const void *d_views, int n, const void *const *h_ptrs, int same_w,
                           cudaStream_t st);  // kb200_moments_slab.cu
 
+int kb200_gemm_slab_try(int M, int Ds, int nsets, int accumulate, long long N, long long in_r, long long out_r, const void *d_views, int n,
+                        const void *const *h_ptrs, int same_w, cudaStream_t st);  // kb200_scatter_slab.cu
+
 int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, int nsets, int accumulate, const void *d_views,
                           int n, const void *const *h_ptrs, int n_ptrs, int same_w, cudaStream_t st) {
   if (layout != 0 && layout != 1 && layout != 2 && layout != 4) return -1;
@@ -450,6 +453,12 @@ int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, i
   gm.nkc4 = (gm.K + 3) / 4;
   const int Kp = gm.nkc4 * 4;
   const MomentsDescK *dv = (const MomentsDescK *)d_views;
+  // LPlusTimes with a long reduction (M >= 36: fp64-bound, BASELINE config 3) and one contiguous run of columns per chunk:
+  // the producer/consumer-group kernel of kb200_scatter_slab.cu as a plain product
+  if (mode == 1 && gm.K >= 36 && gm.B == 1 && gm.pack_N == 0 && n_ptrs == n * (nsets + 1)) {
+    const int rc = kb200_gemm_slab_try(M, Ds, nsets, accumulate, gm.N, gm.in_r, gm.out_r, d_views, n, h_ptrs, same_w, st);
+    if (rc != -1) return rc;
+  }
   // regime: all outputs in registers with K streamed, or K resident with output passes
   if (gm.q <= 4 || (gm.q <= 13 && Kp > 32)) {
     gm.KC = Kp < 16 ? Kp : 16;

@@ -28,6 +28,7 @@ namespace kb200 {
 struct SlabGeom {
   int M, Zs, K, nkc4, Otot, CS, ngroups;
   int nst, ntn, nslots, accumulate;
+  int nmat, unit;       // matrices per Legendre order (3 materials); unit = 1: a single matrix, every fraction 1 (kb200_gemm_slab_try)
   int exp;              // timing experiments (KB200_SLAB_EXP): 1 no tensor-core work, 2 no copies, 4 no stores -- wrong results
   long long in_b;       // moment stride of phi / phi_out (elements)
   int ntiles;           // M * ngroups * ntn
@@ -170,17 +171,18 @@ __global__ void __launch_bounds__(32 * (WO * WN + 1) * NG, 1) scatter_slab_kerne
         if (!__all_sync(0xffffffffu, ok)) lockstep = false;  // a sibling is not keeping up (not resident?): stop waiting for it
       }
       const double *const *rows = tb.inrow + (size_t)grp * 4 * gm.nkc4;
-      const double *frow = tb.frac + (size_t)grp * 3 * gm.Zs + z0;
+      const double *frow = gm.unit ? nullptr : tb.frac + (size_t)grp * 3 * gm.Zs + z0;
+      const int nfr = gm.unit ? 0 : 3;  // fraction rows riding in the stage
       const long long off = (long long)b * gm.in_b + z0;
       for (int st = 0; st < gm.nst; ++st, ++it) {
         const unsigned s = it % SL_STAGES, ph = (it / SL_STAGES) & 1u;
         sl_mb_wait(empty0 + 8u * s, ph ^ 1u);
         const int nrows = min(KC, gm.K - st * KC);
         if (gm.exp & 2) { if (lane == 0) sl_mb_arrive(full0 + 8u * s); continue; }
-        if (lane == 0) sl_mb_expect_tx(full0 + 8u * s, (unsigned)(nrows + 3) * rb);
+        if (lane == 0) sl_mb_expect_tx(full0 + 8u * s, (unsigned)(nrows + nfr) * rb);
         __syncwarp();
         const unsigned sb = ring0 + s * SL_STAGE_BYTES;
-        for (int rr = lane; rr < nrows + 3; rr += 32) {
+        for (int rr = lane; rr < nrows + nfr; rr += 32) {
           if (rr < nrows) sl_bulk_g2s(sb + (unsigned)rr * PITCH, rows[st * KC + rr] + off, rb, full0 + 8u * s);
           else sl_bulk_g2s(sb + FRAC_OFF + (unsigned)(rr - nrows) * PITCH, frow + (size_t)(rr - nrows) * gm.Zs, rb, full0 + 8u * s);
         }
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(32 * (WO * WN + 1) * NG, 1) scatter_slab_kerne
   const int wg = warp - grpw * GW;
   const int wo = wg / WN, wn = wg - wo * WN;
   const int col0 = wn * 16, jq = lane >> 2, kq = lane & 3;
-  const unsigned a_lane = sl_smem(Ws) + (unsigned)(wo * 3 * gm.nkc4 * 32) * (8u * QP) + 16u * lane;
+  const unsigned a_lane = sl_smem(Ws) + (unsigned)(wo * gm.nmat * gm.nkc4 * 32) * (8u * QP) + 16u * lane;
   const unsigned b_lane = (unsigned)kq * PITCH + (unsigned)(col0 + 2 * jq) * 8u;
   const int ncta = (gm.ntiles - slot + gm.nslots - 1) / gm.nslots;  // tiles of this CTA: t = slot + i * nslots
   bool first = true;
@@ -205,9 +207,10 @@ __global__ void __launch_bounds__(32 * (WO * WN + 1) * NG, 1) scatter_slab_kerne
   int op_grp = -1;
   for (int b_lo = 0; b_lo < gm.M;) {
     // the moments [b_lo, b_hi) share their Legendre order, i.e. the material matrices
-    const int n_leg = __ldg(tb.m2l + b_lo);
+    const int n_leg = gm.unit ? 0 : __ldg(tb.m2l + b_lo);
     int b_hi = b_lo + 1;
-    while (b_hi < gm.M && __ldg(tb.m2l + b_hi) == n_leg) ++b_hi;
+    if (gm.unit) b_hi = gm.M;
+    else while (b_hi < gm.M && __ldg(tb.m2l + b_hi) == n_leg) ++b_hi;
     const int i_lo = (max(b_lo * per_b - slot, 0) + gm.nslots - 1) / gm.nslots;
     const int i_hi = min(ncta, (max(b_hi * per_b - slot, 0) + gm.nslots - 1) / gm.nslots);
     b_lo = b_hi;
@@ -241,7 +244,8 @@ __global__ void __launch_bounds__(32 * (WO * WN + 1) * NG, 1) scatter_slab_kerne
         sl_mb_wait(full0 + 8u * s, ph);
         const int kc_lo = st * (KC / 4), nkc = min(KC / 4, gm.nkc4 - kc_lo);
         const unsigned fa0 = sb + FRAC_OFF + (unsigned)(col0 + 2 * jq) * 8u;
-        if (st == 0) {  // which materials occur in this warp's 16 zones (every stage of the tile carries the same fraction rows)
+        if (gm.unit) present = 1u;
+        else if (st == 0) {  // which materials occur in this warp's 16 zones (every stage of the tile carries the same fraction rows)
           const double2 f0 = sl_lds128(fa0), f1 = sl_lds128(fa0 + PITCH), f2 = sl_lds128(fa0 + 2 * PITCH);
           const unsigned mine = ((f0.x != 0.0 || f0.y != 0.0) ? 1u : 0u) | ((f1.x != 0.0 || f1.y != 0.0) ? 2u : 0u) |
                                 ((f2.x != 0.0 || f2.y != 0.0) ? 4u : 0u);
@@ -252,11 +256,11 @@ __global__ void __launch_bounds__(32 * (WO * WN + 1) * NG, 1) scatter_slab_kerne
 #pragma unroll 1
         for (int m = 0; m < 3; ++m) {
           if (!((present >> m) & 1u)) continue;
-          const double2 fm = sl_lds128(fa0 + (unsigned)m * PITCH);
+          const double2 fm = gm.unit ? make_double2(1.0, 1.0) : sl_lds128(fa0 + (unsigned)m * PITCH);
           unsigned ap = a_lane + (unsigned)((m * gm.nkc4 + kc_lo) * 32) * (8u * QP);
           unsigned bp = sb + b_lane;
           // all 16 zones pure in this material (the usual case): the B fragments need no scaling
-          const bool pure = __all_sync(0xffffffffu, fm.x == 1.0 && fm.y == 1.0);
+          const bool pure = gm.unit || __all_sync(0xffffffffu, fm.x == 1.0 && fm.y == 1.0);
           auto pass = [&](auto scaled) {
 #pragma unroll 4
             for (int kc = 0; kc < nkc; ++kc, ap += 32u * 8u * QP, bp += 4u * PITCH) {
@@ -310,6 +314,32 @@ __global__ void __launch_bounds__(32 * (WO * WN + 1) * NG, 1) scatter_slab_kerne
         }
       }
     }
+  }
+}
+
+struct GemmDescK {  // = MomentsDescK of kb200_moments*.cu: pointer tables inside the device copy of the ABI descriptor
+  const double *const *w;
+  const double *const *in;
+  double *const *out;
+};
+// fragment-major weights of the plain product out[o][n] = sum_k W[o][k] in[k][n], W[o][k] = w[o / Ds][(o % Ds) * M + k]
+// (LPlusTimes: o = direction, k = moment): wg[(c*WO + wo)][kc][a/2][lane][a%2], one matrix, no Legendre orders
+__global__ void gemm_matrices_kernel(const GemmDescK *__restrict__ descs, int Ds, int M, int O, int K, int CS, int WO, int QP, int nkc4,
+                                     double *__restrict__ wg) {
+  const GemmDescK d0 = descs[0];
+  const long long total = (long long)CS * WO * nkc4 * 32 * QP;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int a0 = (int)(r % 2); r /= 2;
+    const int lane = (int)(r % 32); r /= 32;
+    const int a = 2 * (int)(r % (QP / 2)) + a0; r /= QP / 2;
+    const int kc = (int)(r % nkc4); r /= nkc4;
+    const int wo = (int)(r % WO); r /= WO;
+    const int c = (int)r;
+    const int o = (c * WO + wo) * 8 * QP + 8 * a + (lane >> 2), k = 4 * kc + (lane & 3);
+    double v = 0.0;
+    if (o < O && k < K) v = d0.w[o / Ds][(size_t)(o % Ds) * M + k];
+    wg[idx] = v;
   }
 }
 
@@ -383,6 +413,7 @@ int kb200_scatter_slab_try(const kb200_scattering_desc *h, int n, const void *d_
   if ((long long)M * ngroups * gm.ntn > 0x3fffffffLL) return -1;
   gm.ntiles = M * ngroups * gm.ntn;
   gm.ws_doubles = 3u * nkc4 * 32 * QP * WO;
+  gm.nmat = 3; gm.unit = 0;
   long long nslots = sm_count() / CS;
   if (nslots > gm.ntiles) nslots = gm.ntiles;
   gm.nslots = (int)nslots;
@@ -460,4 +491,87 @@ int kb200_scatter_slab_try(const kb200_scattering_desc *h, int n, const void *d_
   }
 #undef SL_LAUNCH
   return post_launch("scatter_slab");
+}
+
+static unsigned long long g_gemm_slab_launches = 0;
+extern "C" unsigned long long kb200_lplustimes_slab_launches(void) { return g_gemm_slab_launches; }
+
+// Plain product on the slab kernel (one matrix, unit fractions, one "moment" batch): LPlusTimes where the reduction is long
+// enough for it (M >= 36: the fp64-bound regime of BASELINE config 3) and the columns of a chunk are one contiguous run.
+// out rows: o = direction over all sets; in rows: k = moment.  h_ptrs: per chunk the phi_out pointer, then the nsets rhs
+// pointers.  Returns 0 if handled, -1 if this path does not apply, >0 on error.
+int kb200_gemm_slab_try(int M, int Ds, int nsets, int accumulate, long long N, long long in_r, long long out_r, const void *d_views, int n,
+                        const void *const *h_ptrs, int same_w, cudaStream_t st) {
+  const char *env = getenv("KB200_GEMM_SLAB");
+  if (env && env[0] == '0') return -1;
+  const int O = nsets * Ds, K = M, nkc4 = (K + 3) / 4, Kp = 4 * nkc4;
+  if (!same_w || n <= 0 || N % 4 != 0 || O % 32 != 0 || N > 0x3fffffffLL) return -1;
+  if ((in_r * 8) % 16 != 0 || (out_r * 8) % 32 != 0) return -1;
+  for (int i = 0; i < n; ++i)
+    for (int s = 0; s < nsets; ++s)
+      if (((uintptr_t)h_ptrs[(size_t)i * (nsets + 1) + 1 + s] & 31) != 0) return -1;
+  const size_t smem_cap = 227 * 1024 - 4 * SL_STAGES * (size_t)sl_stage_bytes(64, 4) - 256;
+  int Octa = 0;
+  if (O % 64 == 0 && (size_t)Kp * 64 * 8 <= smem_cap) Octa = 64;
+  else if ((size_t)Kp * 32 * 8 <= smem_cap) Octa = 32;
+  else return -1;
+  const int CS = O / Octa;
+  if (CS > 32 || CS > sm_count()) return -1;
+  const int WO = Octa / 32, QP = 4, NG = 4;
+  const int WN = 16 / NG / WO, NT = 16 * WN, KC = sl_stage_rows(NT, NG);
+  SlabGeom gm;
+  memset(&gm, 0, sizeof(gm));
+  gm.M = 1; gm.Zs = (int)N; gm.K = K; gm.nkc4 = nkc4; gm.Otot = O; gm.CS = CS; gm.ngroups = n;
+  gm.nst = (K + KC - 1) / KC; gm.ntn = (int)((N + NT - 1) / NT); gm.accumulate = accumulate; gm.source = 0.0;
+  gm.in_b = 0;
+  if ((long long)n * gm.ntn > 0x3fffffffLL) return -1;
+  gm.ntiles = n * gm.ntn;
+  gm.nmat = 1; gm.unit = 1;
+  gm.ws_doubles = (unsigned)nkc4 * 32 * QP * WO;
+  long long nslots = sm_count() / CS;
+  if (nslots > gm.ntiles) nslots = gm.ntiles;
+  gm.nslots = (int)nslots;
+
+  std::vector<const void *> tab((size_t)n * Kp + (size_t)n * O);
+  for (int i = 0; i < n; ++i) {
+    const void *const *p = h_ptrs + (size_t)i * (nsets + 1);
+    for (int k = 0; k < Kp; ++k) tab[(size_t)i * Kp + k] = k < K ? (const void *)((const double *)p[0] + (long long)k * in_r) : nullptr;
+    for (int o = 0; o < O; ++o)
+      tab[(size_t)n * Kp + (size_t)i * O + o] = (const void *)((const double *)p[1 + o / Ds] + (long long)(o % Ds) * out_r);
+  }
+  const void *d_tab = nullptr;
+  int rc = device_descs(tab.data(), tab.size() * sizeof(void *), &d_tab, st);
+  if (rc) return rc;
+  const size_t wg_b = (size_t)CS * gm.ws_doubles * sizeof(double);
+  const size_t prog_b = ((size_t)gm.nslots * CS * 4 * sizeof(unsigned) + 255) & ~(size_t)255;
+  const size_t need = wg_b + prog_b;
+  if (g_slab_scratch_bytes < need) {
+    if (g_slab_scratch) { KB_CUDA(cudaDeviceSynchronize()); cudaFree(g_slab_scratch); g_slab_scratch = nullptr; g_slab_scratch_bytes = 0; }
+    KB_CUDA(cudaMalloc(&g_slab_scratch, need));
+    g_slab_scratch_bytes = need;
+  }
+  unsigned char *sc = reinterpret_cast<unsigned char *>(g_slab_scratch);
+  SlabTables tb;
+  memset(&tb, 0, sizeof(tb));
+  tb.wg = reinterpret_cast<const double *>(sc);
+  tb.progress = reinterpret_cast<unsigned *>(sc + wg_b);
+  tb.inrow = reinterpret_cast<const double *const *>(d_tab);
+  tb.orow = (double *const *)((const void *const *)d_tab + (size_t)n * Kp);
+  const long long wtotal = (long long)CS * gm.ws_doubles;
+  gemm_matrices_kernel<<<(unsigned)((wtotal + 255) / 256 > 1184 ? 1184 : (wtotal + 255) / 256), 256, 0, st>>>(
+      (const GemmDescK *)d_views, Ds, M, O, K, CS, WO, QP, nkc4, reinterpret_cast<double *>(sc));
+  rc = post_launch("gemm_matrices");
+  if (rc) return rc;
+  if (CS > 1) KB_CUDA(cudaMemsetAsync(tb.progress, 0, prog_b, st));
+  const size_t smem = (size_t)gm.ws_doubles * 8 + NG * (SL_STAGES * (size_t)sl_stage_bytes(NT, NG) + 16 * SL_STAGES);
+  const unsigned grid = (unsigned)(gm.nslots * CS);
+  if (WO == 2) {
+    KB_CUDA(cudaFuncSetAttribute(scatter_slab_kernel<4, 2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scatter_slab_kernel<4, 2, 2, 4><<<grid, 32 * (2 * 2 + 1) * 4, smem, st>>>(gm, tb);
+  } else {
+    KB_CUDA(cudaFuncSetAttribute(scatter_slab_kernel<4, 1, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scatter_slab_kernel<4, 1, 4, 4><<<grid, 32 * (1 * 4 + 1) * 4, smem, st>>>(gm, tb);
+  }
+  ++g_gemm_slab_launches;
+  return post_launch("gemm_slab");
 }

@@ -77,6 +77,8 @@ MOMENT_SHAPES = [
     # kb200_moments_mma.cu; M = 100 the wide-output / streamed-K paths; M = 1 the degenerate one
     (4, 96), (9, 16), (0, 8), (5, 40),
     (4, 192),  # BASELINE config 2's shape per direction set (Ds = 24, M = 25): 16-byte fragment loads + the DFMA column/row
+    (5, 64),   # M = 36, 64 directions: LPlusTimes as a plain product on the slab kernel (kb200_gemm_slab_try), 64 outputs per CTA
+    (9, 256),  # M = 100, 256 directions: the same with four sibling CTAs of 64 outputs (BASELINE config 3's regime)
 ]
 
 
@@ -84,6 +86,9 @@ MOMENT_SHAPES = [
 @pytest.mark.parametrize("shape", range(len(MOMENT_SHAPES)))
 def test_moments_tensor_core_shapes(gpu, shape, layout):
     L, quad = MOMENT_SHAPES[shape]
+    if (L, quad) == (9, 256) and layout in ("GZD", "ZGD"):
+        pytest.skip("3-group sets are too narrow for the row-operand tensor kernel and the DFMA row kernel's 256-row tile needs "
+                    "256*(Ds+M)*8 B = 281 KB of shared memory at M = 100: the library refuses loudly (DESIGN section 8)")
     args = f"--zones 10,6,8 --groups 6 --quad {quad} --legendre {L} --gset 2 --dset 8 --zset 1,2,1 --layout {layout}"
     p, o, _, _ = pair(gpu, args)
     A = gpu.abi()
@@ -95,10 +100,13 @@ def test_moments_tensor_core_shapes(gpu, shape, layout):
     assert_close(p.field("phi"), o.field("phi"), f"LTimes L={L} {layout}", False)
     # M = 25 with contiguous (group, zone) columns runs on the producer/consumer-group kernel of kb200_moments_slab.cu
     assert (A.kb200_ltimes_slab_launches() > slab0) == (L == 4 and layout in ("DGZ", "DZG", "GDZ")), (L, layout)
+    A.kb200_lplustimes_slab_launches.restype = C.c_ulonglong
+    slab1 = A.kb200_lplustimes_slab_launches()
     fill_both(p, o, "phi_out", 1200 + shape, -1.0, 1.0)
     o.zero("rhs"); o.lplustimes()
     p.call("zero:rhs"); p.call("LPlusTimes")
     assert_close(p.field("rhs"), o.field("rhs"), f"LPlusTimes L={L} {layout}", False)
+    assert (A.kb200_lplustimes_slab_launches() > slab1) == (L >= 5 and quad % 32 == 0 and layout in ("DGZ", "DZG")), (L, quad, layout)
     # accumulate semantics (no pending zero-fill): a second call adds on top
     o.ltimes(); p.call("LTimes")
     assert_close(p.field("phi"), o.field("phi"), f"LTimes accumulate L={L} {layout}", False)
