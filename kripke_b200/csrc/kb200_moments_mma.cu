@@ -459,6 +459,12 @@ int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, i
     const int rc = kb200_gemm_slab_try(M, Ds, nsets, accumulate, gm.N, gm.in_r, gm.out_r, d_views, n, h_ptrs, same_w, st);
     if (rc != -1) return rc;
   }
+  // LTimes with M = 25 * c moments: producer warps + consumer groups, c sibling CTAs of 24 + 1 moments (kb200_moments_slab.cu)
+  if (mode == 0 && M % 25 == 0 && gm.pack_N == 0 && n_ptrs == n * (nsets + 1)) {
+    const int rc = kb200_ltimes_slab_try(M, Ds, nsets, accumulate, gm.B, gm.N, gm.in_b, gm.in_r, gm.out_b, gm.out_r, d_views, n, h_ptrs,
+                                         same_w, st);
+    if (rc != -1) return rc;
+  }
   // regime: all outputs in registers with K streamed, or K resident with output passes
   if (gm.q <= 4 || (gm.q <= 13 && Kp > 32)) {
     gm.KC = Kp < 16 ? Kp : 16;
@@ -466,11 +472,6 @@ int kb200_moments_mma_try(int mode, int layout, int M, int Ds, int Gs, int Zs, i
     gm.npass = 1;
     gm.ntn = (gm.N + 127) / 128;
     if (gm.q == 4 && gm.O == 25) {  // 3 tensor-core tiles + one DFMA row instead of 4 tiles (22% less fp64 work)
-      if (mode == 0 && gm.pack_N == 0 && n_ptrs == n * (nsets + 1)) {  // producer warps + consumer groups (kb200_moments_slab.cu)
-        const int rc = kb200_ltimes_slab_try(M, Ds, nsets, accumulate, gm.B, gm.N, gm.in_b, gm.in_r, gm.out_b, gm.out_r, d_views, n, h_ptrs,
-                                             same_w, st);
-        if (rc != -1) return rc;
-      }
       gm.q = 3;
       const char *e = getenv("KB200_LTIMES_KC");
       const int kc = e ? atoi(e) : 32;

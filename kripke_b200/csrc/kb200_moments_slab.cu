@@ -1,5 +1,6 @@
-// LTimes at M = 25 (Legendre order 4) for the nestings whose (group, zone) plane is contiguous per direction (DGZ, DZG, GDZ),
-// default arithmetic.  Reference: src/Kripke/Kernel/LTimes.cpp:54-65.
+// LTimes at M = 25 * c moments (Legendre order 4: c = 1; order 9: c = 4 sibling CTAs of 25 moments each that walk the same tiles
+// in advisory lockstep, so the siblings' reads of a tile meet in L2) for the nestings whose (group, zone) plane is contiguous
+// per direction (DGZ, DZG, GDZ), default arithmetic.  Reference: src/Kripke/Kernel/LTimes.cpp:54-65.
 //
 //   phi(nm, n) (+)= sum_k ell(nm, k) * psi(k, n)        k = all directions of all sets, n = a run of (group, zone) columns
 //
@@ -32,12 +33,14 @@ struct MomentsDescK {  // same as in kb200_moments.cu
 
 struct MsGeom {
   int M, Ds, K, nkc4, nst, accumulate, adj;
+  int CS, nslots;             // sibling CTAs per tile sequence (25 moments each: M = 25 * CS), tile sequences of the launch
   int ntn, per_desc, ntiles;  // column tiles per batch, tiles per descriptor, tiles of the call
   long long N, in_b, out_b;   // columns per batch; batch strides of psi and phi
 };
 struct MsTables {
   const double *const *inrow;  // [ndesc][nst*KC] direction rows of psi (batch 0, column 0), nullptr beyond K
-  double *const *orow;         // [ndesc][25]     moment rows of phi
+  double *const *orow;         // [ndesc][M]      moment rows of phi
+  unsigned *progress;          // [nslots][CS][groups] tiles issued by each sibling's producers (CS > 1 only)
 };
 
 __device__ __forceinline__ unsigned ms_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -74,6 +77,8 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ltimes_slab_kernel(const Moment
   const unsigned stage0 = ms_smem(msl) + ws_b;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = warp < NW ? warp / MS_WN : warp - NW;  // consumer group of this warp / the group this producer feeds
+  // M = 25 * CS moments: CS sibling CTAs walk the same tiles, each with its own 25 moments (24 + 1) of the weights
+  const int slot = (int)blockIdx.x / gm.CS, sib = (int)blockIdx.x - slot * gm.CS;
   const unsigned ring0 = stage0 + (unsigned)grp * (MS_STAGES * MS_STAGE_BYTES);
   const unsigned full0 = stage0 + MS_NG * MS_STAGES * MS_STAGE_BYTES + (unsigned)grp * (16u * MS_STAGES), empty0 = full0 + 8u * MS_STAGES;
 
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ltimes_slab_kernel(const Moment
       double v = 0.0;
       if (k < gm.K) {
         const int s = k / gm.Ds, d = k - s * gm.Ds;
-        const int o = (a < 3) ? 8 * a + (l >> 2) : 24;
+        const int o = 25 * sib + ((a < 3) ? 8 * a + (l >> 2) : 24);
         v = d0.w[s][(size_t)d * gm.M + o];
       }
       Ws[idx] = v;
@@ -104,12 +109,23 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ltimes_slab_kernel(const Moment
   __syncthreads();
 
   // this group's tiles: the groups of a CTA work on neighbouring tiles (KB200_MS_ADJ=1; default: a grid apart, measured equal or better)
-  const int first = gm.adj ? MS_NG * (int)blockIdx.x + grp : (int)blockIdx.x + grp * (int)gridDim.x, step = MS_NG * (int)gridDim.x;
+  const int first = gm.adj ? MS_NG * slot + grp : slot + grp * gm.nslots, step = MS_NG * gm.nslots;
   if (warp >= NW) {
     // ---- producer of group grp: one bulk copy per direction row of a stage ----
-    unsigned it = 0;
-    for (int t = first; t < gm.ntiles; t += step) {
+    unsigned it = 0, done = 0;
+    bool lockstep = gm.CS > 1;
+    for (int t = first; t < gm.ntiles; t += step, ++done) {
       const int dsc = t / gm.per_desc, r = t - dsc * gm.per_desc, b = r / gm.ntn, tn = r - b * gm.ntn;
+      if (lockstep && done > 0) {  // advisory: stay within a tile of the siblings so that their reads of this tile meet in L2
+        bool ok = true;
+        if (lane < gm.CS && lane != sib) {
+          const volatile unsigned *p = tb.progress + ((size_t)slot * gm.CS + lane) * MS_NG + grp;
+          int polls = 0;
+          while (*p + 1u < done && ++polls < 512) {}
+          ok = polls < 512;
+        }
+        if (!__all_sync(0xffffffffu, ok)) lockstep = false;
+      }
       const long long n0 = (long long)tn * MS_NT;
       const long long rem = gm.N - n0;
       const unsigned rb = 8u * (unsigned)(rem < MS_NT ? rem : MS_NT);
@@ -123,6 +139,10 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ltimes_slab_kernel(const Moment
         __syncwarp();
         if (lane < nrows)
           ms_bulk_g2s(ring0 + s * MS_STAGE_BYTES + (unsigned)lane * MS_PITCH, rows[st * MS_KC + lane] + off, rb, full0 + 8u * s);
+      }
+      if (gm.CS > 1 && lane == 0) {
+        __threadfence();
+        *(volatile unsigned *)(tb.progress + ((size_t)slot * gm.CS + sib) * MS_NG + grp) = done + 1u;
       }
     }
     return;
@@ -165,7 +185,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ltimes_slab_kernel(const Moment
     }
 
     // epilogue: lane holds moments 8a + jq at the four consecutive columns col0 + 4*kq + {0,1,2,3} ...
-    double *const *orow = tb.orow + (size_t)dsc * 25;
+    double *const *orow = tb.orow + (size_t)dsc * gm.M + 25 * sib;
     const long long ob = (long long)b * gm.out_b + (long long)tn * MS_NT + col0;
     const long long n4 = (long long)tn * MS_NT + col0 + 4 * kq;
     if (n4 < gm.N) {
@@ -210,7 +230,9 @@ int kb200_ltimes_slab_try(int M, int Ds, int nsets, int accumulate, long long B,
                           cudaStream_t st) {
   const char *env = getenv("KB200_LTIMES_SLAB");
   if (env && env[0] == '0') return -1;
-  if (M != 25 || !same_w || N % 4 != 0 || n <= 0) return -1;
+  if (M % 25 != 0 || M > 200 || !same_w || N % 4 != 0 || n <= 0) return -1;
+  const int CS = M / 25;
+  if (CS > sm_count()) return -1;
   const int K = nsets * Ds, nkc4 = (K + 3) / 4, nst = (K + MS_KC - 1) / MS_KC;
   const size_t smem = (size_t)nkc4 * 1024 + (size_t)MS_NG * (MS_STAGES * MS_STAGE_BYTES + 16 * MS_STAGES);
   if (smem > 227 * 1024) return -1;
@@ -229,12 +251,12 @@ int kb200_ltimes_slab_try(int M, int Ds, int nsets, int accumulate, long long B,
 
   // host-built row tables, uploaded through the descriptor cache
   const size_t Kp = (size_t)nst * MS_KC;
-  std::vector<const void *> tab((size_t)n * Kp + (size_t)n * 25);
+  std::vector<const void *> tab((size_t)n * Kp + (size_t)n * M);
   for (int i = 0; i < n; ++i) {
     const void *const *p = h_ptrs + (size_t)i * (nsets + 1);
     for (size_t k = 0; k < Kp; ++k)
       tab[(size_t)i * Kp + k] = k < (size_t)K ? (const void *)((const double *)p[k / Ds] + (long long)(k % Ds) * in_r) : nullptr;
-    for (int o = 0; o < 25; ++o) tab[(size_t)n * Kp + (size_t)i * 25 + o] = (const void *)((const double *)p[nsets] + (long long)o * out_r);
+    for (int o = 0; o < M; ++o) tab[(size_t)n * Kp + (size_t)i * M + o] = (const void *)((const double *)p[nsets] + (long long)o * out_r);
   }
   const void *d_tab = nullptr;
   int rc = device_descs(tab.data(), tab.size() * sizeof(void *), &d_tab, st);
@@ -244,9 +266,18 @@ int kb200_ltimes_slab_try(int M, int Ds, int nsets, int accumulate, long long B,
   tb.orow = (double *const *)((const void *const *)d_tab + (size_t)n * Kp);
 
   KB_CUDA(cudaFuncSetAttribute(ltimes_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int ctas = sm_count();
-  if (ctas > gm.ntiles) ctas = gm.ntiles;
-  ltimes_slab_kernel<<<ctas, MS_THREADS, smem, st>>>((const MomentsDescK *)d_views, gm, tb);
+  int nslots = sm_count() / CS;
+  if (nslots > gm.ntiles) nslots = gm.ntiles;
+  gm.CS = CS; gm.nslots = nslots;
+  tb.progress = nullptr;
+  if (CS > 1) {  // advisory progress counters of the siblings
+    static unsigned *d_prog = nullptr;
+    const size_t pb = (size_t)sm_count() * MS_NG * sizeof(unsigned);
+    if (!d_prog) KB_CUDA(cudaMalloc(&d_prog, pb));
+    KB_CUDA(cudaMemsetAsync(d_prog, 0, pb, st));
+    tb.progress = d_prog;
+  }
+  ltimes_slab_kernel<<<nslots * CS, MS_THREADS, smem, st>>>((const MomentsDescK *)d_views, gm, tb);
   ++g_ltimes_slab_launches;
   return post_launch("ltimes_slab");
 }

@@ -98,8 +98,8 @@ def test_moments_tensor_core_shapes(gpu, shape, layout):
     o.zero("phi"); o.ltimes()
     p.call("zero:phi"); p.call("LTimes")
     assert_close(p.field("phi"), o.field("phi"), f"LTimes L={L} {layout}", False)
-    # M = 25 with contiguous (group, zone) columns runs on the producer/consumer-group kernel of kb200_moments_slab.cu
-    assert (A.kb200_ltimes_slab_launches() > slab0) == (L == 4 and layout in ("DGZ", "DZG", "GDZ")), (L, layout)
+    # M = 25 (or 100 = 4 sibling CTAs of 25 moments) with contiguous (group, zone) columns runs on kb200_moments_slab.cu
+    assert (A.kb200_ltimes_slab_launches() > slab0) == (L in (4, 9) and layout in ("DGZ", "DZG", "GDZ")), (L, layout)
     A.kb200_lplustimes_slab_launches.restype = C.c_ulonglong
     slab1 = A.kb200_lplustimes_slab_launches()
     fill_both(p, o, "phi_out", 1200 + shape, -1.0, 1.0)
