@@ -177,10 +177,10 @@ __global__ void __launch_bounds__(128) moments_col_kernel(const Desc *__restrict
 // rows x OT outputs in registers, and the output tile goes back through shared memory so the
 // stores are coalesced as well.
 // ------------------------------------------------------------------------------------------------
-template <int OTP, bool EXACT, typename Desc>
+template <int OTP, bool EXACT, typename Desc, int RT>  // RT rows per block: 256 (2 per thread), 128, or 64 where the tile must shrink
 __global__ void __launch_bounds__(128) moments_row_kernel(const Desc *__restrict__ descs, MomentsGeom gm) {
   extern __shared__ __align__(16) double smem[];
-  constexpr int RT = 256;                // rows per block (2 per thread)
+  constexpr bool HAS_B = RT == 256;
   const Desc &dsc = descs[blockIdx.y];
   const int M = gm.M, Ds = gm.Ds;
   const int Kc = (gm.mode == 0) ? Ds : M;        // inputs per row per in-chunk
@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(128) moments_row_kernel(const Desc *__restrict
   const int n_in_chunks = (gm.mode == 0) ? gm.nsets : 1;
   const int n_out_chunks = (gm.mode == 0) ? 1 : gm.nsets;
   const int tiles_per_chunk = gm.ntiles_o;
-  const int ra = threadIdx.x, rb = threadIdx.x + 128;
+  const bool has_a = (int)threadIdx.x < RT;               // RT = 64: the upper half of the block only helps with the copies
+  const int ra = has_a ? (int)threadIdx.x : 0, rb = HAS_B ? (int)threadIdx.x + 128 : ra;
 
   for (int oc = 0; oc < n_out_chunks; ++oc) {
     for (int t = 0; t < tiles_per_chunk; ++t) {
@@ -244,8 +245,8 @@ __global__ void __launch_bounds__(128) moments_row_kernel(const Desc *__restrict
 #pragma unroll
       for (int i = 0; i < OTP; ++i)
         if (i < on) {
-          out_s[ra * OcP + o0 + i] = acc[i][0];
-          out_s[rb * OcP + o0 + i] = acc[i][1];
+          if (has_a) out_s[ra * OcP + o0 + i] = acc[i][0];
+          if (HAS_B) out_s[rb * OcP + o0 + i] = acc[i][1];
         }
     }
     __syncthreads();
@@ -319,16 +320,23 @@ static int launch_col(const MomentsDescK *d_descs, int n, const MomentsGeom &gm,
   return post_launch("moments_col");
 }
 
-template <int OTP, bool EXACT>
-static int launch_row(const MomentsDescK *d_descs, int n, const MomentsGeom &gm, cudaStream_t st) {
-  int Kc = (gm.mode == 0) ? gm.Ds : gm.M, Oc = (gm.mode == 0) ? gm.M : gm.Ds;
-  size_t smem = ((size_t)256 * (Kc | 1) + (size_t)256 * (Oc | 1) + (size_t)Kc * OTP) * sizeof(double);
-  KB_REQUIRE(smem <= 220 * 1024, "moments_row: tile needs %zu bytes of shared memory", smem);
-  dim3 grid((unsigned)((gm.R + 255) / 256), n, 1);
-  auto k = moments_row_kernel<OTP, EXACT, MomentsDescK>;
+template <int OTP, bool EXACT, int RT>
+static int launch_row_t(const MomentsDescK *d_descs, int n, const MomentsGeom &gm, size_t smem, cudaStream_t st) {
+  dim3 grid((unsigned)((gm.R + RT - 1) / RT), n, 1);
+  auto k = moments_row_kernel<OTP, EXACT, MomentsDescK, RT>;
   KB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   k<<<grid, 128, smem, st>>>(d_descs, gm);
   return post_launch("moments_row");
+}
+template <int OTP, bool EXACT>
+static int launch_row(const MomentsDescK *d_descs, int n, const MomentsGeom &gm, cudaStream_t st) {
+  int Kc = (gm.mode == 0) ? gm.Ds : gm.M, Oc = (gm.mode == 0) ? gm.M : gm.Ds;
+  // the largest row tile whose staging fits: 256 rows, or 128 / 64 for long rows (M = 100 with 32 directions per set)
+  auto need = [&](int rt) { return ((size_t)rt * (Kc | 1) + (size_t)rt * (Oc | 1) + (size_t)Kc * OTP) * sizeof(double); };
+  if (need(256) <= 220 * 1024) return launch_row_t<OTP, EXACT, 256>(d_descs, n, gm, need(256), st);
+  if (need(128) <= 220 * 1024) return launch_row_t<OTP, EXACT, 128>(d_descs, n, gm, need(128), st);
+  KB_REQUIRE(need(64) <= 220 * 1024, "moments_row: tile needs %zu bytes of shared memory", need(64));
+  return launch_row_t<OTP, EXACT, 64>(d_descs, n, gm, need(64), st);
 }
 
 

@@ -78,7 +78,8 @@ MOMENT_SHAPES = [
     (4, 96), (9, 16), (0, 8), (5, 40),
     (4, 192),  # BASELINE config 2's shape per direction set (Ds = 24, M = 25): 16-byte fragment loads + the DFMA column/row
     (5, 64),   # M = 36, 64 directions: LPlusTimes as a plain product on the slab kernel (kb200_gemm_slab_try), 64 outputs per CTA
-    (9, 256),  # M = 100, 256 directions: the same with four sibling CTAs of 64 outputs (BASELINE config 3's regime)
+    (9, 256),  # M = 100, 256 directions: the same with four sibling CTAs of 64 outputs (BASELINE config 3's regime); in GZD/ZGD the
+               # 3-group sets are too narrow for the row-operand tensor kernel: the DFMA row kernel with a 128-row tile
 ]
 
 
@@ -86,9 +87,6 @@ MOMENT_SHAPES = [
 @pytest.mark.parametrize("shape", range(len(MOMENT_SHAPES)))
 def test_moments_tensor_core_shapes(gpu, shape, layout):
     L, quad = MOMENT_SHAPES[shape]
-    if (L, quad) == (9, 256) and layout in ("GZD", "ZGD"):
-        pytest.skip("3-group sets are too narrow for the row-operand tensor kernel and the DFMA row kernel's 256-row tile needs "
-                    "256*(Ds+M)*8 B = 281 KB of shared memory at M = 100: the library refuses loudly (DESIGN section 8)")
     args = f"--zones 10,6,8 --groups 6 --quad {quad} --legendre {L} --gset 2 --dset 8 --zset 1,2,1 --layout {layout}"
     p, o, _, _ = pair(gpu, args)
     A = gpu.abi()
