@@ -198,6 +198,9 @@ int kb200_sweep_population_uniform(const kb200_sweep_desc *h_descs, int n, const
 const char *kb200_last_sweep_kernel(void);
 /* *d_result = sum of d_partials[0..n) in index order (fixed-order tree, deterministic) */
 int kb200_population_reduce(const double *d_partials, int n, double *d_result, kb200_stream_t stream);
+/* *h_value = the common value of d_v[0..n) if all n doubles are equal and positive, else 0 (synchronises the stream; the host
+ * layer uses it to recognise a uniform zone-volume field for kb200_sweep_population_uniform without downloading the field) */
+int kb200_uniform_positive_value(const double *d_v, size_t n, double *h_value, kb200_stream_t stream);
 
 /* ---- layout transform (remaining nestings via transform) --------------------------
  * Re-orders a 3-index field (a,b,c extents in canonical <Direction|Moment, Group, Zone> order)

@@ -274,6 +274,14 @@ __global__ void __launch_bounds__(256) layout_transform_tiled_kernel(int nf, int
   }
 }
 
+// Is every element of v[0..n) equal to v[0]?  flag[0] = number of blocks that saw a different value.
+__global__ void uniform_check_kernel(const double *__restrict__ v, size_t n, unsigned *__restrict__ flag) {
+  const double first = __ldg(v);
+  bool differ = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) differ |= (__ldg(v + i) != first);
+  if (__syncthreads_or(differ) && threadIdx.x == 0) atomicAdd(flag, 1u);
+}
+
 }  // namespace kb200
 
 using namespace kb200;
@@ -361,6 +369,30 @@ int kb200_population_reduce(const double *d_partials, int n, double *d_result, k
   KB_REQUIRE(d_result && (d_partials || n <= 0), "kb200_population_reduce: null pointer");
   population_final_kernel<<<1, 256, 0, resolve_stream(stream)>>>(d_partials, n > 0 ? n : 0, d_result, 0);
   return post_launch("population_final");
+}
+
+// *h_value = the common value of d_v[0..n) if all n doubles are bit-equal and positive, else 0.  Synchronises the stream
+// (12 bytes come back instead of the whole array): used by the host layer to recognise a uniform zone-volume field.
+int kb200_uniform_positive_value(const double *d_v, size_t n, double *h_value, kb200_stream_t stream) {
+  KB_REQUIRE(h_value && (d_v || n == 0), "kb200_uniform_positive_value: null pointer");
+  *h_value = 0.0;
+  if (n == 0) return 0;
+  cudaStream_t st = resolve_stream(stream);
+  static unsigned *d_flag = nullptr;
+  if (!d_flag) KB_CUDA(cudaMalloc(&d_flag, sizeof(unsigned)));
+  KB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(unsigned), st));
+  size_t blocks = (n + 1023) / 1024;
+  if (blocks > 592) blocks = 592;
+  uniform_check_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_v, n, d_flag);
+  int rc = post_launch("uniform_check");
+  if (rc) return rc;
+  unsigned differ = 1;
+  double first = 0.0;
+  KB_CUDA(cudaMemcpyAsync(&differ, d_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  KB_CUDA(cudaMemcpyAsync(&first, d_v, sizeof(double), cudaMemcpyDeviceToHost, st));
+  KB_CUDA(cudaStreamSynchronize(st));
+  if (!differ && first > 0.0) *h_value = first;
+  return 0;
 }
 
 int kb200_population(const kb200_population_desc *h, int n, double *d_scratch, double *d_result, kb200_stream_t stream) {

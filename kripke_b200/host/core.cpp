@@ -436,12 +436,18 @@ double FieldStorageBase::uniformPositiveValue(SdomId sdom_id) {
   size_t ci = m_subdomain_to_chunk[*sdom_id];
   if (m_elem_size != sizeof(double)) return 0.0;
   if (m_chunks[ci].uniform_epoch != m_chunks[ci].write_epoch) {
-    const double *v = (const double *)hostPtr(sdom_id, false);
     Chunk &c = m_chunks[ci];
     const size_t n = m_chunk_to_size[ci];
-    double u = n ? v[0] : 0.0;
-    for (size_t i = 1; i < n && u > 0.0; ++i)
-      if (v[i] != u) u = 0.0;
+    double u = 0.0;
+    if (c.dev && c.dev_valid && !c.host_valid && !c.zero_pending) {
+      // the current contents live on the device only (written there by a kernel or an upload): ask the device
+      KB200_CALL(kb200_uniform_positive_value((const double *)c.dev, n, &u, nullptr));
+    } else {
+      const double *v = (const double *)hostPtr(sdom_id, false);
+      u = n ? v[0] : 0.0;
+      for (size_t i = 1; i < n && u > 0.0; ++i)
+        if (v[i] != u) u = 0.0;
+    }
     c.uniform_value = (u > 0.0) ? u : 0.0;
     c.uniform_epoch = c.write_epoch;
   }
