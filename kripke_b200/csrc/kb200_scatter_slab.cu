@@ -8,17 +8,20 @@
 // and it works in slabs of 16 source groups: 380 instructions per warp and slab around 32 DMMAs.  This kernel
 // * groups the descriptors that read the same source chunks (all destination group sets of one zone set) and lets one
 //   CTA produce ALL their outputs from one staged tile [K source groups][NT zones];
-// * stages whole K x NT tiles (32 KB stages, 4 deep) with bulk-TMA row copies issued by a producer warp; eight consumer
-//   warps own (output block, 16-zone column block) pairs and run mma.sync.m8n8k4.f64 with both operands fetched by
-//   128-bit shared loads (zones 2j/2j+1 of a column block are the two B fragments of lane group j, so one load feeds
-//   two DMMAs and an accumulator lane ends up with four consecutive zones = one 32-byte store);
+// * stages the tiles through bulk-TMA row copies: sixteen consumer warps in NG groups (four groups of 2 x 2 warps by default),
+//   every group with its own producer warp and its own 3-stage ring ([KC source groups][NT zones] plus the tile's three
+//   material-fraction rows per stage); the groups take the CTA's tiles in turn, so one group's epilogue overlaps the
+//   other groups' DMMAs.  A consumer warp owns an (output block, 16-zone column block) pair and runs mma.sync.m8n8k4.f64
+//   with both operands fetched by 128-bit shared loads (zones 2j/2j+1 of a column block are the two B fragments of lane
+//   group j, so one load feeds two DMMAs and an accumulator lane ends up with four consecutive zones = one 32-byte store);
 // * keeps the three material matrices of the current Legendre order resident (fragment-major, prebuilt once per call
 //   in global scratch and copied when the order changes; tiles are walked moment-major so that is L+1 times per CTA);
 // * where the matrices of all outputs do not fit (config 3: 3 x 128 x 128 doubles), CS sibling CTAs take 32-output
 //   chunks of the same tile sequence and keep within a tile of each other (advisory progress counters in global
 //   memory, never a correctness dependency), so the siblings' re-reads of a tile hit L2.
 // Anything this kernel does not cover (odd shapes, unaligned chunks, irregular descriptor lists) returns -1 and the
-// per-descriptor kernel of kb200_scatter_mma.cu runs instead.
+// per-descriptor kernel of kb200_scatter_mma.cu runs instead.  The same kernel serves LPlusTimes with a long reduction as a
+// plain product (kb200_gemm_slab_try: one matrix, unit fractions).
 #include <type_traits>
 #include <vector>
 #include "kb200_common.cuh"
