@@ -127,6 +127,9 @@ int kb200_scattering(const kb200_scattering_desc *h_descs, int n, kb200_stream_t
  * receives strength * (volume fraction of material 0 in the zone).  *folded = 1: done, kb200_source must not follow;
  * *folded = 0: the kernel in use cannot fold (bit-exact mode, odd shapes) and only the scattering was done. */
 int kb200_scattering_source(const kb200_scattering_desc *h_descs, int n, double strength, int *folded, kb200_stream_t stream);
+/* What a scattering call would do with this descriptor list, without a device: 0 = the one-read kernel takes it (descriptor
+ * groups sharing their source chunks, destination groups per CTA, sibling CTAs per tile sequence), -1 = declined. */
+int kb200_scattering_plan(const kb200_scattering_desc *h_descs, int n, int *ngroups, int *outputs_per_cta, int *siblings);
 /* kernel family that served the last scattering call: "slab", "mma", "transposed+slab", "transposed+mma" or "dfma" */
 const char *kb200_last_scattering_kernel(void);
 

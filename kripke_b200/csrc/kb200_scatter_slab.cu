@@ -354,23 +354,27 @@ static size_t g_slab_scratch_bytes = 0;
 using namespace kb200;
 
 // Returns 0 if handled, -1 if this path does not apply (the caller goes on to the per-descriptor kernel), >0 on error.
-int kb200_scatter_slab_try(const kb200_scattering_desc *h, int n, const void *d_descs, int sigs_layout, double source, cudaStream_t st) {
+// What the slab kernel would do with a list of descriptors: pure host logic (no CUDA call), also exported for the CPU tests.
+struct SlabPlan {
+  int ngroups = 0, nd = 0, Otot = 0, K = 0, Octa = 0, CS = 0;
+  std::vector<int> first;                  // first descriptor of each group
+  std::vector<std::vector<int>> members;   // descriptors of each group, in call order
+};
+static bool slab_plan(const kb200_scattering_desc *h, int n, int sms, SlabPlan &pl) {
   const int layout = h[0].layout;
-  if (layout != 0 && layout != 2) return -1;
-  const char *env = getenv("KB200_SCATTER_SLAB");
-  if (env && env[0] == '0') return -1;
-  const int Zs = h[0].Zs, Gs = h[0].Gs, M = h[0].M, nsrc = h[0].nsrc;
-  if (Zs % 4 != 0) return -1;
+  if (layout != 0 && layout != 2) return false;
+  const int Zs = h[0].Zs, Gs = h[0].Gs, nsrc = h[0].nsrc;
+  if (Zs % 4 != 0) return false;
   // descriptor groups: same source chunks and zone tables (= the destination group sets of one zone set)
-  std::vector<int> group_of(n), first;
-  std::vector<std::vector<int>> members;
+  std::vector<int> &first = pl.first;
+  std::vector<std::vector<int>> &members = pl.members;
   for (int i = 0; i < n; ++i) {
     if (h[i].nsrc != nsrc || h[i].accumulate != h[0].accumulate || h[i].G != h[0].G || h[i].L1 != h[0].L1 || h[i].sigs != h[0].sigs ||
         h[i].moment_to_legendre != h[0].moment_to_legendre)
-      return -1;
-    if (((uintptr_t)h[i].phi_out & 31) != 0) return -1;
+      return false;
+    if (((uintptr_t)h[i].phi_out & 31) != 0) return false;
     for (int s = 0; s < nsrc; ++s)
-      if (((uintptr_t)h[i].phi_src[s] & 15) != 0) return -1;
+      if (((uintptr_t)h[i].phi_src[s] & 15) != 0) return false;
     int g = -1;
     for (size_t q = 0; q < first.size() && g < 0; ++q) {
       const kb200_scattering_desc &f = h[first[q]];
@@ -381,27 +385,50 @@ int kb200_scatter_slab_try(const kb200_scattering_desc *h, int n, const void *d_
     }
     if (g < 0) { g = (int)first.size(); first.push_back(i); members.emplace_back(); }
     members[g].push_back(i);
-    group_of[i] = g;
   }
   const int ngroups = (int)first.size(), nd = (int)members[0].size();
   for (int g = 0; g < ngroups; ++g) {
-    if ((int)members[g].size() != nd) return -1;
+    if ((int)members[g].size() != nd) return false;
     for (int q = 0; q < nd; ++q) {
-      if (h[members[g][q]].glower_dst != h[members[0][q]].glower_dst) return -1;
+      if (h[members[g][q]].glower_dst != h[members[0][q]].glower_dst) return false;
       for (int s = 0; s < nsrc; ++s)
-        if (h[members[g][q]].glower_src[s] != h[members[0][0]].glower_src[s]) return -1;
+        if (h[members[g][q]].glower_src[s] != h[members[0][0]].glower_src[s]) return false;
     }
   }
-  const int Otot = nd * Gs, K = nsrc * Gs, nkc4 = (K + 3) / 4, Kp = 4 * nkc4;
-  if (Otot % 32 != 0) return -1;
+  const int Otot = nd * Gs, K = nsrc * Gs, Kp = 4 * ((K + 3) / 4);
+  if (Otot % 32 != 0) return false;
   // outputs per CTA: everything in one CTA if the three matrices fit next to the stages, else 32-output sibling chunks
-  const size_t smem_cap = 227 * 1024 - 4 * SL_STAGES * (size_t)sl_stage_bytes(64, 4) - 256;  // the largest rings of the variants below
+  const size_t smem_cap = 227 * 1024 - 4 * SL_STAGES * (size_t)sl_stage_bytes(64, 4) - 256;  // the largest rings of the variants
   int Octa = 0;
   if (Otot % 64 == 0 && (size_t)3 * Kp * 64 * 8 <= smem_cap) Octa = 64;
   else if ((size_t)3 * Kp * 32 * 8 <= smem_cap) Octa = 32;
-  else return -1;
+  else return false;
   const int CS = Otot / Octa;
-  if (CS > 32 || CS > sm_count()) return -1;
+  if (CS > 32 || CS > sms) return false;
+  pl.ngroups = ngroups; pl.nd = nd; pl.Otot = Otot; pl.K = K; pl.Octa = Octa; pl.CS = CS;
+  return true;
+}
+// 0: the list runs on the slab kernel, with *ngroups descriptor groups, *outputs_per_cta destination groups per CTA and
+// *siblings CTAs per tile sequence; -1: it is declined (per-descriptor kernel).  Needs no device.
+extern "C" int kb200_scattering_plan(const kb200_scattering_desc *h, int n, int *ngroups, int *outputs_per_cta, int *siblings) {
+  if (!h || n <= 0) return -1;
+  SlabPlan pl;
+  if (!slab_plan(h, n, sm_count() > 0 ? sm_count() : 148, pl)) return -1;
+  if (ngroups) *ngroups = pl.ngroups;
+  if (outputs_per_cta) *outputs_per_cta = pl.Octa;
+  if (siblings) *siblings = pl.CS;
+  return 0;
+}
+
+int kb200_scatter_slab_try(const kb200_scattering_desc *h, int n, const void *d_descs, int sigs_layout, double source, cudaStream_t st) {
+  const char *env = getenv("KB200_SCATTER_SLAB");
+  if (env && env[0] == '0') return -1;
+  SlabPlan pl;
+  if (!slab_plan(h, n, sm_count(), pl)) return -1;
+  const int layout = h[0].layout, Zs = h[0].Zs, Gs = h[0].Gs, M = h[0].M;
+  const std::vector<int> &first = pl.first;
+  const std::vector<std::vector<int>> &members = pl.members;
+  const int ngroups = pl.ngroups, Otot = pl.Otot, K = pl.K, nkc4 = (K + 3) / 4, Kp = 4 * nkc4, Octa = pl.Octa, CS = pl.CS;
   const int WO = Octa / 32, QP = 4;
   int NG = 4;  // consumer groups taking the tiles of a CTA in turn (16 consumer warps in all; 8 with a single group)
   { const char *we = getenv("KB200_SLAB_GROUPS"); if (we && (atoi(we) == 1 || atoi(we) == 2)) NG = atoi(we); }
