@@ -14,7 +14,7 @@ cut -c1-400 $O/${TAG}_bench_config2_DGZ.json
 for lay in GZD ZGD; do
   timeout 600 python bench.py --steps 10 --warmup 3 --layout $lay --no-cpu-baseline > $O/${TAG}_bench_config2_${lay}.json 2>> $O/${TAG}_bench.err
 done
-#timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_reference_arm.json 2>> $O/${TAG}_bench.err
+timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_reference_arm.json 2>> $O/${TAG}_bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_config2_DGZ.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'sweep_|moments_|ltimes_slab|scatter_|population' --launch-skip 6 -c 6 -o /tmp/${TAG}_full_config2_DGZ python tools/gpu_probe.py config2:DGZ > $O/${TAG}_full_dgz.log 2>&1
 python tools/ncu_summary.py /tmp/${TAG}_full_config2_DGZ.ncu-rep > $O/${TAG}_ncu_full_config2_DGZ_summary.txt 2>&1
